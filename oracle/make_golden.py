@@ -1,0 +1,168 @@
+"""ORACLE support — generate tests/golden/*.npz from the REAL reference.
+
+Run in the build container (needs /root/reference):
+    python oracle/make_golden.py
+Imports the unmodified reference modules (oracle/refshim.py), feeds them the
+deterministic synthetic weights / inputs of `voice-tts_b200/synth.py`, and
+stores inputs + reference outputs as small fixtures.  The reference ships no
+tests or golden vectors, so these files are what pins
+the oracle (and through it the CUDA path) to the reference.
+"""
+import contextlib
+import importlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # noqa: E402
+
+synth = importlib.import_module("voice-tts_b200.synth")
+config = importlib.import_module("voice-tts_b200.config")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+ACT_CASES = [
+    # name, B, C, T, kind, logscale, input scale
+    ("tiny_t1", 1, 2, 1, "snakebeta", True, 1.0),
+    ("tiny_t2", 1, 3, 2, "snakebeta", True, 1.0),
+    ("short_t7", 2, 3, 7, "snakebeta", True, 1.0),
+    ("odd_t37", 2, 3, 37, "snakebeta", True, 1.0),
+    ("c24_t64", 1, 24, 64, "snakebeta", True, 1.0),
+    ("c5_t257", 1, 5, 257, "snakebeta", True, 3.0),
+    ("snake_t100", 1, 4, 100, "snake", True, 1.0),
+    ("linear_t50", 1, 4, 50, "snakebeta", False, 1.0),
+    ("c48_t1024", 1, 48, 1024, "snakebeta", True, 2.0),
+]
+
+
+def act_inputs(name, B, C, T, scale):
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = torch.randn(B, C, T, generator=g) * scale
+    a = torch.randn(C, generator=g) * 0.5
+    b = torch.randn(C, generator=g) * 0.5
+    return x, a, b
+
+
+def gen_activation(mod):
+    from indextts.s2mel.modules.bigvgan import activations
+    from indextts.s2mel.modules.bigvgan.alias_free_activation.torch.act import Activation1d
+    from indextts.s2mel.modules.bigvgan.alias_free_activation.torch.filter import kaiser_sinc_filter1d
+    out = {"taps": kaiser_sinc_filter1d(0.25, 0.3, 12).reshape(-1).numpy()}
+    for name, B, C, T, kind, logscale, scale in ACT_CASES:
+        x, a, b = act_inputs(name, B, C, T, scale)
+        if kind == "snakebeta":
+            act = activations.SnakeBeta(C, alpha_logscale=logscale)
+        else:
+            act = activations.Snake(C, alpha_logscale=logscale)
+        if not logscale:
+            a, b = torch.exp(a), torch.exp(b)
+        with torch.no_grad():
+            act.alpha.copy_(a)
+            if kind == "snakebeta":
+                act.beta.copy_(b)
+        m = Activation1d(activation=act).eval()
+        with torch.no_grad():
+            y = m(x)
+            y64 = m.double()(x.double())
+        out[name + ".x"] = x.numpy()
+        out[name + ".alpha"] = a.numpy()
+        out[name + ".beta"] = (b if kind == "snakebeta" else a).numpy()
+        out[name + ".y"] = y.numpy()
+        out[name + ".y64"] = y64.numpy()
+    np.savez_compressed(os.path.join(OUT, "activation1d.npz"), **out)
+    print("activation1d.npz:", len(ACT_CASES), "cases")
+
+
+def gen_ampblock(mod):
+    out = {}
+    for C, k, T in ((16, 3, 90), (16, 7, 90), (8, 11, 130)):
+        h = mod.AttrDict(dict(config.default_hparams()))
+        with contextlib.redirect_stdout(io.StringIO()):
+            blk = mod.AMPBlock1(h, C, k, (1, 3, 5), activation="snakebeta")
+            blk.remove_weight_norm()
+        g = torch.Generator().manual_seed(100 * C + k)
+        sd = {}
+        for key, v in blk.state_dict().items():
+            if key.endswith("filter"):
+                sd[key] = v.clone()
+            elif "act." in key:
+                sd[key] = torch.randn(v.shape, generator=g) * 0.5
+            else:
+                fan = C * k
+                sd[key] = (torch.rand(v.shape, generator=g) * 2 - 1) / fan ** 0.5
+        blk.load_state_dict(sd)
+        x = torch.randn(2, C, T, generator=g)
+        with torch.no_grad():
+            y = blk.eval()(x)
+        tag = "c%d_k%d" % (C, k)
+        out[tag + ".x"] = x.numpy()
+        out[tag + ".y"] = y.numpy()
+        for key, v in sd.items():
+            out[tag + ".sd." + key] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "ampblock1.npz"), **out)
+    print("ampblock1.npz")
+
+
+def sd_fingerprint(sd):
+    """Per-state-dict drift detector for the seeded generator."""
+    s1 = sum(float(v.double().sum()) for v in sd.values())
+    s2 = sum(float(v.double().abs().sum()) for v in sd.values())
+    return np.array([s1, s2, float(len(sd))])
+
+
+def gen_generators(mod):
+    out = {}
+    cases = [
+        ("tiny", config.tiny_hparams(), 7, 2, 21),
+        ("tiny_tanh_bias", config.tiny_hparams(use_tanh_at_final=True, use_bias_at_final=True), 8, 1, 9),
+        ("full", config.default_hparams(), 1234, 1, 40),
+    ]
+    for name, h, seed, B, T in cases:
+        sd = synth.make_state_dict(h, seed=seed)
+        m = refshim.build_generator(h, sd)
+        mel = synth.make_mel(B, h["num_mels"], T)
+        with torch.no_grad():
+            wav = m(mel)
+        out[name + ".mel"] = mel.numpy()
+        out[name + ".wav"] = wav.numpy()
+        out[name + ".sd_fingerprint"] = sd_fingerprint(sd)
+        out[name + ".seed"] = np.array([seed])
+        print(name, tuple(mel.shape), "->", tuple(wav.shape), "absmax %.4f" % wav.abs().max())
+        if name == "tiny":
+            # weight-normed checkpoint form of the same model: g = ||v||, v = weight
+            with contextlib.redirect_stdout(io.StringIO()):
+                m2 = mod.BigVGAN(mod.AttrDict(dict(h)))
+            wn = {}
+            for key, v in m2.state_dict().items():
+                base = key[:-9] if key.endswith((".weight_g", ".weight_v")) else None
+                if key.endswith(".weight_v"):
+                    wn[key] = sd[base + ".weight"] * 0.5
+                elif key.endswith(".weight_g"):
+                    w = sd[base + ".weight"]
+                    wn[key] = w.reshape(w.shape[0], -1).norm(dim=1).reshape(v.shape)
+                else:
+                    wn[key] = sd[key]
+            m2.load_state_dict(wn)
+            with torch.no_grad():
+                wav2 = m2.eval()(mel)
+            out["tiny.wav_weightnorm"] = wav2.numpy()
+            print("  weight-normed form max diff %.2e" % (wav2 - wav).abs().max())
+    np.savez_compressed(os.path.join(OUT, "generators.npz"), **out)
+
+
+def main():
+    assert refshim.available(), "reference tree not found"
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(OUT, exist_ok=True)
+    mod = refshim.load()
+    gen_activation(mod)
+    gen_ampblock(mod)
+    gen_generators(mod)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+"""CPU tests: the oracle against the golden vectors produced by the real
+reference (oracle/make_golden.py), against the survey's known-answer facts
+(SURVEY.md 8(c)), and - when /root/reference is present - against the reference
+itself."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigvgan_oracle as O
+from oracle import refshim
+from oracle.make_golden import ACT_CASES, sd_fingerprint
+
+TAP_BITS = [0x3B04F861, 0x3C19D646, 0xBCD14084, 0xBD6C2A26, 0x3E03A888, 0x3EE2EC65]
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_filter_taps_bit_patterns(golden, synth):
+    g = golden("activation1d")["taps"]
+    for taps in (O.kaiser_taps().numpy(), synth.kaiser_sinc_filter1d().reshape(-1).numpy()):
+        bits = taps.view(np.uint32)
+        assert list(bits[:6]) == TAP_BITS
+        assert list(bits[6:]) == TAP_BITS[::-1]          # symmetric f[k] = f[11-k]
+        assert np.array_equal(taps, g)
+    assert abs(float(g[0::2].sum()) - 0.5) < 1e-7 and abs(float(g[1::2].sum()) - 0.5) < 1e-7
+
+
+@pytest.mark.parametrize("case", ACT_CASES, ids=[c[0] for c in ACT_CASES])
+def test_activation1d_vs_reference_golden(golden, case):
+    name, B, C, T, kind, logscale, scale = case
+    g = golden("activation1d")
+    x, a, b = t(g[name + ".x"]), t(g[name + ".alpha"]), t(g[name + ".beta"])
+    taps = t(g["taps"])
+    y64 = O.activation1d(x.double(), a.double(), b.double(), taps.double(), taps.double(), logscale)
+    assert (y64 - t(g[name + ".y64"])).abs().max() < 1e-12
+    y32 = O.activation1d(x, a, b, taps, taps, logscale)
+    assert (y32 - t(g[name + ".y"])).abs().max() < 2e-6 * max(1.0, float(x.abs().max()))
+    ys = O.activation1d_staged(x.double(), a.double(), b.double(), taps.double(), taps.double(), logscale)
+    assert (ys - y64).abs().max() < 1e-12
+
+
+def test_activation1d_dc_gain_and_linearity():
+    # zero periodic part (beta -> +inf) makes the operator a pure up/down FIR
+    # cascade: constants pass through exactly (unit DC gain incl. replicate edges)
+    taps = O.kaiser_taps(dtype=torch.float64)
+    x = torch.full((1, 2, 33), 0.75, dtype=torch.float64)
+    big = torch.full((2,), 40.0, dtype=torch.float64)
+    y = O.activation1d(x, torch.zeros(2, dtype=torch.float64), big, taps, taps)
+    assert (y - 0.75).abs().max() < 1e-12
+    x1, x2 = torch.randn(1, 2, 50, dtype=torch.float64), torch.randn(1, 2, 50, dtype=torch.float64)
+    f = lambda z: O.activation1d(z, torch.zeros(2, dtype=torch.float64), big, taps, taps)
+    assert (f(x1 + 2 * x2) - f(x1) - 2 * f(x2)).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("tag", ["c16_k3", "c16_k7", "c8_k11"])
+def test_ampblock1_vs_reference_golden(golden, cfg, tag):
+    g = golden("ampblock1")
+    sd = {k[len(tag) + 4:]: t(g[k]) for k in g.files if k.startswith(tag + ".sd.")}
+    sd = {"rb." + k: v for k, v in sd.items()}
+    h = cfg.default_hparams()
+    y = O.amp_block1(sd, "rb", t(g[tag + ".x"]), h, (1, 3, 5))
+    assert (y - t(g[tag + ".y"])).abs().max() < 5e-6
+
+
+def test_conv_index_maps():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 6, 40, generator=g, dtype=torch.float64)
+    for k, d in ((3, 1), (7, 3), (11, 5)):
+        w = torch.randn(5, 6, k, generator=g, dtype=torch.float64)
+        b = torch.randn(5, generator=g, dtype=torch.float64)
+        assert (O.conv1d(x, w, b, d) - O.conv1d_indexed(x, w, b, d)).abs().max() < 1e-12
+    for u in (2, 4):
+        w = torch.randn(6, 3, 2 * u, generator=g, dtype=torch.float64)
+        b = torch.randn(3, generator=g, dtype=torch.float64)
+        y = O.conv_transpose1d(x, w, b, u)
+        assert y.shape[-1] == u * 40
+        assert (y - O.conv_transpose1d_polyphase(x, w, b, u)).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_tanh_bias", "full"])
+def test_generator_vs_reference_golden(golden, synth, cfg, name):
+    g = golden("generators")
+    h = {"tiny": cfg.tiny_hparams(),
+         "tiny_tanh_bias": cfg.tiny_hparams(use_tanh_at_final=True, use_bias_at_final=True),
+         "full": cfg.default_hparams()}[name]
+    sd = synth.make_state_dict(h, seed=int(g[name + ".seed"][0]))
+    # the seeded weights are the ones the reference saw when the golden was made
+    assert np.allclose(sd_fingerprint(sd), g[name + ".sd_fingerprint"], rtol=1e-9)
+    wav = O.generator_forward(sd, h, t(g[name + ".mel"]))
+    ref = t(g[name + ".wav"])
+    assert wav.shape == ref.shape
+    assert (wav - ref).abs().max() < 1e-5 * max(1.0, float(ref.abs().max()))
+    if name == "tiny":
+        assert (wav - t(g["tiny.wav_weightnorm"])).abs().max() < 1e-5
+
+
+def test_fold_weight_norm():
+    v = torch.randn(4, 3, 5)
+    g = torch.rand(4, 1, 1) + 0.5
+    w = O.fold_weight_norm({"c.weight_g": g, "c.weight_v": v, "c.bias": torch.zeros(4)})["c.weight"]
+    assert torch.allclose(w.reshape(4, -1).norm(dim=1), g.reshape(-1), atol=1e-6)
+
+
+def test_survey_counts(synth, cfg):
+    h = cfg.default_hparams()
+    spec = synth.state_dict_spec(h)
+    assert len(spec) == 667
+    n = sum(int(np.prod(s)) for k, s, kind in spec if kind != "filter")
+    assert n == 112_199_472
+    assert cfg.macs_per_frame(h) == 901_859_328
+    assert cfg.act_elems_per_frame(h) == 614_400
+
+
+def test_receptive_field(synth, cfg):
+    """Changing one mel frame alters only +-34 frames of output (SURVEY.md 8(c)
+    golden fact 4), checked on the tiny generator scaled accordingly."""
+    h = cfg.tiny_hparams()
+    sd = synth.make_state_dict(h, seed=7)
+    mel = synth.make_mel(1, h["num_mels"], 120)
+    mel2 = mel.clone()
+    mel2[:, :, 60] += 1.0
+    up = cfg.total_upsample(h)
+    d = (O.generator_forward(sd, h, mel) - O.generator_forward(sd, h, mel2)).abs().reshape(-1)
+    nz = torch.nonzero(d > 0).reshape(-1)
+    assert int(nz.min()) >= (60 - 34) * up and int(nz.max()) < (60 + 35) * up
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+def test_oracle_matches_live_reference(synth, cfg):
+    h = cfg.tiny_hparams()
+    sd = synth.make_state_dict(h, seed=11)
+    m = refshim.build_generator(h, sd)
+    mel = synth.make_mel(1, h["num_mels"], 13)
+    with torch.no_grad():
+        ref = m(mel)
+    assert (O.generator_forward(sd, h, mel) - ref).abs().max() < 2e-6
+    assert set(m.state_dict().keys()) == set(sd.keys())
