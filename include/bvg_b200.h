@@ -1,0 +1,153 @@
+/*
+ * bvg_b200.h — C ABI of libbvg_b200.so: the BigVGAN v2 vocoder hot path of
+ * caishiqing/voice-tts (IndexTTS2), hand-written CUDA for sm_100a (B200).
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain
+ * pointers / sizes / a CUDA stream handle (no torch or C++ types), returns 0 on
+ * success or a negative BVG_E* code, and never throws.  `bvg_last_error()`
+ * returns a thread-local message for the last failure.  All buffers are owned
+ * by the caller unless stated; the library only owns what `bvg_create`
+ * allocates (packed weights + workspace) and frees it in `bvg_destroy`.
+ * There is no CPU fallback: with no sm_100 device every compute entry point
+ * fails with BVG_ENODEV.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   bvg_act1d_fwd        <- pybind `anti_alias_activation_cuda.forward(input, up_ftr, down_ftr, alpha, beta)`
+ *                           indextts/s2mel/modules/bigvgan/alias_free_activation/cuda/anti_alias_activation.cpp:19-23
+ *                           -> `fwd_cuda` anti_alias_activation_cuda.cu:212-246, called from
+ *                           cuda/activation1d.py:21-27 (FusedAntiAliasActivation.forward); semantics of
+ *                           torch/act.py:25-30 (replicate-pad edges exactly as the torch path)
+ *   bvg_conv1d_fwd       <- torch.nn.Conv1d as built at bigvgan.py:59-66,76-83,285-287,348-350
+ *   bvg_convtr1d_fwd     <- torch.nn.ConvTranspose1d as built at bigvgan.py:306-312
+ *   bvg_create/..._fwd   <- BigVGAN.__init__/forward/remove_weight_norm  bigvgan.py:266-400,
+ *                           called from indextts/infer_v2.py:155-158,735
+ *   bvg_vocoder_fwd_host <- the host round trip of indextts/infer_v2.py:735-744 (mel on host -> wav on host,
+ *                           optional int16 quantisation `clamp(32767*wav)` of :740)
+ */
+#ifndef BVG_B200_H_
+#define BVG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVG_ABI_VERSION 1
+
+/* status codes */
+#define BVG_OK 0
+#define BVG_EINVAL (-1)   /* bad shape / argument / NULL pointer          */
+#define BVG_EDTYPE (-2)   /* unsupported dtype                            */
+#define BVG_EALIGN (-3)   /* pointer not aligned as documented            */
+#define BVG_ECUDA (-4)    /* CUDA runtime/driver error (see last_error)   */
+#define BVG_ENODEV (-5)   /* no sm_100 device / kernel image not loadable */
+#define BVG_ENOMEM (-6)   /* device or host allocation failed             */
+#define BVG_ESTATE (-7)   /* handle not finalized / weight missing        */
+
+/* element types of activations at the ABI */
+#define BVG_F32 0
+#define BVG_BF16 1
+
+/* precision modes of the whole-vocoder handle */
+#define BVG_MODE_FP32 0 /* fp32 storage, fp32 SIMT convs, accurate sin: <=1e-5 rel. vs fp32 reference */
+#define BVG_MODE_BF16 1 /* bf16 conv operands on tcgen05 tensor cores, fp32 accumulate + fp32 residual  */
+
+/* snake kinds */
+#define BVG_SNAKE 0     /* x + 1/(a+1e-9) sin^2(a x)   (activations.py:46-59)   */
+#define BVG_SNAKEBETA 1 /* x + 1/(b+1e-9) sin^2(a x)   (activations.py:107-120) */
+
+typedef void* bvg_stream_t; /* a cudaStream_t (CUstream); NULL = legacy default stream */
+typedef struct bvg_vocoder bvg_vocoder;
+
+int bvg_abi_version(void);
+const char* bvg_last_error(void);
+/* number of kernels this library has launched in the calling process so far */
+uint64_t bvg_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Fused anti-aliased activation: up x2 (12-tap kaiser-sinc, replicate pad 5|5)
+ * -> Snake/SnakeBeta -> down x2 (12-tap, replicate pad 5|6), one kernel.
+ *   dst, src : [B, C, T] contiguous, time fastest (the reference layout), dtype `dtype`
+ *   alpha_log, beta_log : [C] fp32, LOG scale (the kernel applies exp), device
+ *   up_taps, down_taps  : [12] fp32 HOST arrays (Activation1d.upsample.filter / .downsample.lowpass.filter;
+ *                         construction-time constants, passed to the kernel as launch parameters)
+ *   flags : bit0 = use fast sin (MUFU) instead of the accurate one.
+ * T == 0 or B*C == 0 is a no-op that returns BVG_OK (as the reference, .cu:193-196).
+ * dst may not alias src.
+ */
+#define BVG_ACT_FAST_SIN 1
+int bvg_act1d_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                  const float* up_taps, const float* down_taps, int B, int C, int64_t T,
+                  int dtype, int flags, bvg_stream_t stream);
+
+/* Same operator on channels-last data [B, T, C] (the library's internal layout).
+ * in_dtype/out_dtype may differ (fp32 residual stream in, bf16 MMA operand out). */
+int bvg_act1d_cl_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                     const float* up_taps, const float* down_taps, int B, int64_t T, int C,
+                     int in_dtype, int out_dtype, int flags, bvg_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Stand-alone dense layers on the reference layout (used by the parity tests
+ * and by callers that want single layers): fp32 [B,C,T] in/out, fp32 weights in
+ * torch layout.  `mode` selects fp32 SIMT or bf16 tcgen05 arithmetic.
+ *   conv1d   : weight [Cout, Cin, k], bias [Cout] or NULL, zero padding (k-1)*dil/2
+ *   convtr1d : weight [Cin, Cout, k], k == 2*stride, padding stride/2 -> T_out = stride*T
+ */
+int bvg_conv1d_fwd(float* dst, const float* src, const float* weight, const float* bias,
+                   int B, int Cin, int Cout, int64_t T, int k, int dilation, int mode,
+                   bvg_stream_t stream);
+int bvg_convtr1d_fwd(float* dst, const float* src, const float* weight, const float* bias,
+                     int B, int Cin, int Cout, int64_t T, int k, int stride, int mode,
+                     bvg_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Whole generator.  Build: bvg_create -> bvg_set_tensor for every state-dict
+ * tensor (folded weights, reference key names) -> bvg_finalize -> forward calls.
+ */
+typedef struct bvg_config {
+  int num_mels;                 /* 80 */
+  int upsample_initial_channel; /* 1536 */
+  int num_upsamples;            /* <= 8 */
+  int upsample_rates[8];        /* {4,4,2,2,2,2} */
+  int upsample_kernel_sizes[8]; /* {8,8,4,4,4,4}; must equal 2*rate */
+  int num_kernels;              /* <= 4 */
+  int resblock_kernel_sizes[4]; /* {3,7,11} */
+  int num_dilations;            /* <= 4 */
+  int resblock_dilations[4][4]; /* [kernel][layer] {1,3,5} */
+  int snake_kind;               /* BVG_SNAKE / BVG_SNAKEBETA */
+  int snake_logscale;           /* 1: parameters are log-scale */
+  int use_tanh_at_final;
+  int use_bias_at_final;
+  int mode;                     /* BVG_MODE_* */
+  int device;                   /* CUDA device ordinal */
+} bvg_config;
+
+int bvg_create(const bvg_config* cfg, bvg_vocoder** out);
+void bvg_destroy(bvg_vocoder* v);
+/* `name` is a reference state-dict key ("conv_pre.weight", "ups.0.0.bias",
+ * "resblocks.3.convs1.0.weight", "resblocks.3.activations.2.act.alpha",
+ * "activation_post.upsample.filter", "conv_post.weight", ...); `data` is fp32,
+ * contiguous, on the handle's device (is_device=1) or on the host (0); the
+ * library copies/packs it before returning.  numel is checked against the config. */
+int bvg_set_tensor(bvg_vocoder* v, const char* name, const float* data, int64_t numel, int is_device);
+int bvg_finalize(bvg_vocoder* v);
+/* bytes of device workspace needed for (B, T0); grows the handle's arena. */
+int64_t bvg_workspace_bytes(const bvg_vocoder* v, int B, int T0);
+
+/* mel [B, num_mels, T0] fp32 device -> wav [B, 1, T0*prod(rates)] fp32 device, on `stream`. */
+int bvg_vocoder_fwd(bvg_vocoder* v, const float* mel, float* wav, int B, int T0, bvg_stream_t stream);
+/* Host buffers: H2D, forward, D2H on `stream`, then waits for completion.
+ * wav_dtype: 0 = fp32 wav in [-1,1]; 1 = int16 `clamp(32767*wav, -32767, 32767)` (infer_v2.py:740). */
+int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, int wav_dtype,
+                         int B, int T0, bvg_stream_t stream);
+/* options: "graph" (0/1, CUDA-graph the layer sequence), "conv_impl" (0 auto, 1 simt, 2 umma) */
+int bvg_set_option(bvg_vocoder* v, const char* key, int value);
+/* introspection for benchmarks: kernels launched by the last forward */
+int bvg_last_forward_launches(const bvg_vocoder* v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVG_B200_H_ */

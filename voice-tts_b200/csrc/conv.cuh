@@ -1,0 +1,51 @@
+// Internal (non-ABI) interfaces between the translation units of libbvg_b200.
+#pragma once
+#include "common.cuh"
+
+namespace bvg {
+
+// One dense layer on channels-last data (see conv_simt.cu for the formula).
+// A ConvTranspose1d is expressed as a 3-tap conv over the input time axis that
+// writes u*Cout_p "phase channels" per input sample (layout.cu, pack_convtr_kernel).
+struct ConvArgs {
+  const void* in;      // [B, T, Cin_p]
+  const void* w;       // Wp[k][Cout_r][Cin_p]
+  const float* bias;   // [Cout_r] fp32 (zero in pad rows) or nullptr
+  void* out;           // [B, T, out_ld]; channels [0, Cout_n) are written
+  const float* res;    // optional fp32 [B, T, out_ld]
+  const float* accum;  // optional fp32 [B, T, out_ld]
+  float scale;
+  int in_dtype, w_dtype, out_dtype;
+  int B;
+  int64_t T;
+  int Cin_p;    // multiple of 16
+  int Cout_n;   // channels written per row (multiple of 8)
+  int Cout_r;   // rows of Wp per tap (multiple of 128)
+  int out_ld;   // row pitch of out/res/accum in elements
+  int k, dil;
+};
+
+int conv_simt_launch(const ConvArgs& a, cudaStream_t st);
+// tcgen05 implicit-GEMM path: in/w must be bf16.  `variant` selects debug variants (0 = default).
+int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st);
+bool conv_umma_supported(const ConvArgs& a);
+
+int act1d_cl_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,
+                    int B, int64_t T, int C, int in_dtype, int out_dtype, bool fast, cudaStream_t st);
+int act1d_bct_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,
+                     int B, int C, int64_t T, int dtype, bool fast, cudaStream_t st);
+
+int bct_to_btc(void* dst, int out_dtype, const float* src, int B, int C, int Cp, int64_t T, cudaStream_t st);
+int btc_to_bct(float* dst, const void* src, int in_dtype, int B, int C, int Cp, int64_t T, cudaStream_t st);
+int pack_conv_weight(void* wp, int dtype, const float* w, int Cout, int Cin, int k, int Cout_r, int Cin_p,
+                     cudaStream_t st);
+int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int Cout_p, int Cout_r,
+                       int Cin_p, cudaStream_t st);
+int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, const float* w, float bias, int B,
+                     int Cp, int64_t T, int use_tanh, cudaStream_t st);
+int f32_to_i16(int16_t* dst, const float* src, int64_t n, cudaStream_t st);
+
+static inline int pad_channels(int c) { return c < 16 ? 16 : round_up(c, 16); }
+static inline size_t dtype_size(int dt) { return dt == BVG_BF16 ? 2 : 4; }
+
+}  // namespace bvg

@@ -1,0 +1,348 @@
+// Dilated Conv1d / polyphase ConvTranspose1d as an implicit GEMM on the 5th-gen
+// tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+//   D[co, t] = sum_tap sum_ci  Wp[tap][co][ci] * X[t + (tap-center)*dil][ci]
+//
+//   A operand (M = 128 out-channels, K-major)  : weight tile Wp[tap][co0:co0+128][ci0:ci0+KC]   (TMA, per tap)
+//   B operand (N = NT time rows,    K-major)  : activation tile X[t0-halo : t0+NT+halo][ci0:ci0+KC], channels-last
+//   D (fp32, TMEM)                             : 128 lanes (co) x NT columns (t), double buffered (2*NT <= 512 cols)
+//
+// The activation tile (the big operand) is loaded ONCE per input-channel chunk and
+// reused by all k taps: tap j reads the same shared-memory tile through a UMMA
+// descriptor whose start address is advanced by j*dil rows.  Rows are
+// (KC*2)-byte swizzle rows, the hardware swizzle is a function of the absolute
+// shared-memory address, so a whole-row shift keeps TMA's write pattern and
+// UMMA's read pattern consistent.  TMA zero-fills rows outside [0,T) of the
+// 3-D tensor (C, T, B), which is exactly the conv's zero padding, per utterance.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0    : TMA producer (one lane)         -> x_full/x_empty, a_full/a_empty mbarrier rings
+//   warp 1    : TMEM allocator + MMA issuer (one lane), tcgen05.commit frees stages / publishes D
+//   warps 2-5 : epilogue: tcgen05.ld -> (+bias, +residual, *scale, +accum) -> coalesced global stores
+//
+// reference semantics: torch Conv1d/ConvTranspose1d as built in bigvgan.py:59-66,76-83,285-287,306-312.
+#include <cuda.h>
+
+#include "conv.cuh"
+
+namespace bvg {
+
+constexpr int UM_THREADS = 192;
+constexpr int UM_M = 128;
+constexpr int UM_A_STAGES = 6;
+constexpr int UM_X_STAGES = 2;
+constexpr int UM_A_STAGE_BYTES = UM_M * 128;      // 128 rows x (<=128 B)
+constexpr int UM_MAX_X_ROWS = 320;                // NT + (k-1)*dil rounded to 2 boxes of <=160 rows
+constexpr int UM_X_STAGE_BYTES = UM_MAX_X_ROWS * 128;
+constexpr int UM_SMEM_BYTES = 1024 /*align slack*/ + UM_A_STAGES * UM_A_STAGE_BYTES + UM_X_STAGES * UM_X_STAGE_BYTES + 256;
+
+struct UmmaParams {
+  const float* bias;
+  void* out;
+  const float* res;
+  const float* accum;
+  float scale;
+  int out_bf16;
+  int B;
+  int T;
+  int Cin_p, Cout_n, out_ld;
+  int k, dil, center;
+  int KC;            // input channels per chunk: 64 / 32 / 16
+  int nchunks;       // Cin_p / KC
+  int NT;            // time columns per tile (<= 256, multiple of 16)
+  int x_box_rows;    // rows per TMA box of the activation tile (2 boxes per chunk)
+  int n_ttiles, n_cotiles;
+  int64_t n_tiles;   // B * n_ttiles * n_cotiles
+  int base_mode;     // debug: 1 = put (addr>>7)&7 into the descriptor base_offset field
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes, int base_mode) {
+  // K-major, swizzled: SBO = 8 rows; LBO unused (1); version 1 (sm_100)
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+template <bool PER_TAP_X>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const UmmaParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte aligned base (SWIZZLE_128B atoms)
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* a_st = smem;
+  unsigned char* x_st = smem + UM_A_STAGES * UM_A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_st + UM_X_STAGES * UM_X_STAGE_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + UM_A_STAGES;
+  uint64_t* x_full = a_empty + UM_A_STAGES;
+  uint64_t* x_empty = x_full + UM_X_STAGES;
+  uint64_t* t_full = x_empty + UM_X_STAGES;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row_bytes = p.KC * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < UM_A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < UM_X_STAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ntaps = p.k;
+  const uint32_t a_bytes = (uint32_t)UM_M * row_bytes;
+  const uint32_t xbox_bytes = (uint32_t)p.x_box_rows * row_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      uint32_t as = 0, aph = 0, xs = 0, xph = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int cot = (int)(tile % p.n_cotiles);
+        const int64_t r = tile / p.n_cotiles;
+        const int tt = (int)(r % p.n_ttiles);
+        const int b = (int)(r / p.n_ttiles);
+        const int t0 = tt * p.NT;
+        for (int c = 0; c < p.nchunks; ++c) {
+          if (!PER_TAP_X) {
+            mbar_wait(&x_empty[xs], xph ^ 1);
+            mbar_expect_tx(&x_full[xs], 2 * xbox_bytes);
+            unsigned char* dstx = x_st + xs * UM_X_STAGE_BYTES;
+            const int trow = t0 - p.center * p.dil;
+            tma_load_3d(dstx, &tmap_x, c * p.KC, trow, b, &x_full[xs]);
+            tma_load_3d(dstx + xbox_bytes, &tmap_x, c * p.KC, trow + p.x_box_rows, b, &x_full[xs]);
+            if (++xs == UM_X_STAGES) { xs = 0; xph ^= 1; }
+          }
+          for (int j = 0; j < ntaps; ++j) {
+            if (PER_TAP_X) {
+              mbar_wait(&x_empty[xs], xph ^ 1);
+              mbar_expect_tx(&x_full[xs], 2 * xbox_bytes);
+              unsigned char* dstx = x_st + xs * UM_X_STAGE_BYTES;
+              const int trow = t0 + (j - p.center) * p.dil;
+              tma_load_3d(dstx, &tmap_x, c * p.KC, trow, b, &x_full[xs]);
+              tma_load_3d(dstx + xbox_bytes, &tmap_x, c * p.KC, trow + p.x_box_rows, b, &x_full[xs]);
+              if (++xs == UM_X_STAGES) { xs = 0; xph ^= 1; }
+            }
+            mbar_wait(&a_empty[as], aph ^ 1);
+            mbar_expect_tx(&a_full[as], a_bytes);
+            tma_load_3d(a_st + as * UM_A_STAGE_BYTES, &tmap_w, c * p.KC, cot * UM_M, j, &a_full[as]);
+            if (++as == UM_A_STAGES) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) |
+                             ((uint32_t)(UM_M >> 4) << 24);
+      uint32_t as = 0, aph = 0, xs = 0, xph = 0, acc = 0, accph = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        mbar_wait(&t_empty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.NT;
+        uint32_t first = 1;
+        for (int c = 0; c < p.nchunks; ++c) {
+          if (!PER_TAP_X) {
+            mbar_wait(&x_full[xs], xph);
+            tc_fence_after();
+          }
+          for (int j = 0; j < ntaps; ++j) {
+            if (PER_TAP_X) {
+              mbar_wait(&x_full[xs], xph);
+              tc_fence_after();
+            }
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_st + as * UM_A_STAGE_BYTES);
+            uint32_t x_addr = smem_u32(x_st + xs * UM_X_STAGE_BYTES);
+            if (!PER_TAP_X) x_addr += (uint32_t)(j * p.dil) * row_bytes;
+            for (int kk = 0; kk < p.KC / 16; ++kk) {
+              const uint64_t da = make_smem_desc(a_addr + kk * 32, row_bytes, p.base_mode);
+              const uint64_t db = make_smem_desc(x_addr + kk * 32, row_bytes, p.base_mode);
+              umma_f16_ss(d_tmem, da, db, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit(&a_empty[as]);
+            if (++as == UM_A_STAGES) { as = 0; aph ^= 1; }
+            if (PER_TAP_X) {
+              umma_commit(&x_empty[xs]);
+              if (++xs == UM_X_STAGES) { xs = 0; xph ^= 1; }
+            }
+          }
+          if (!PER_TAP_X) {
+            umma_commit(&x_empty[xs]);
+            if (++xs == UM_X_STAGES) { xs = 0; xph ^= 1; }
+          }
+        }
+        umma_commit(&t_full[acc]);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+    }
+  } else {
+    // -------------------------------------------------- epilogue warps 2..5
+    const int g = warp % 4;               // TMEM lane group this warp may access
+    uint32_t acc = 0, accph = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int cot = (int)(tile % p.n_cotiles);
+      const int64_t r = tile / p.n_cotiles;
+      const int tt = (int)(r % p.n_ttiles);
+      const int b = (int)(r / p.n_ttiles);
+      const int t0 = tt * p.NT;
+      const int co = cot * UM_M + g * 32 + lane;
+      const bool warp_active = (cot * UM_M + g * 32) < p.Cout_n;
+      const bool co_ok = co < p.Cout_n;
+      const float bv = (p.bias && co_ok) ? __ldg(p.bias + co) : 0.f;
+
+      mbar_wait(&t_full[acc], accph);
+      tc_fence_after();
+      if (warp_active) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * (uint32_t)p.NT;
+        const int64_t rowbase = ((int64_t)b * p.T + t0) * p.out_ld + co;
+        for (int nb = 0; nb < p.NT; nb += 32) {
+          if (t0 + nb >= p.T) break;
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + nb, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int t = t0 + nb + i;
+            if (t < p.T && co_ok) {
+              const int64_t off = rowbase + (int64_t)(nb + i) * p.out_ld;
+              float y = __uint_as_float(v[i]) + bv;
+              if (p.res) y += __ldg(p.res + off);
+              y *= p.scale;
+              if (p.accum) y += __ldg(p.accum + off);
+              if (p.out_bf16)
+                reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(y);
+              else
+                reinterpret_cast<float*>(p.out)[off] = y;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (++acc == 2) { acc = 0; accph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------ host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                       uint32_t b1, int row_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) BVG_FAIL(BVG_ENODEV, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    BVG_FAIL(BVG_ECUDA, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) box=(%u,%u)", (int)r,
+             (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1);
+  return BVG_OK;
+}
+
+bool conv_umma_supported(const ConvArgs& a) {
+  if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16) return false;
+  if (a.Cin_p % 16 != 0 || a.Cout_r % UM_M != 0) return false;
+  if (a.T <= 0 || a.T > 0x7fffffffLL / 2) return false;
+  if ((a.k - 1) * a.dil > 64) return false;  // activation-tile halo budget (UM_MAX_X_ROWS)
+  if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.w)) & 15) return false;
+  return true;
+}
+
+static int g_sm_count = 0;
+
+int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st) {
+  if (a.B <= 0 || a.T <= 0) return BVG_OK;
+  if (!conv_umma_supported(a)) BVG_FAIL(BVG_EINVAL, "conv_umma: unsupported layer shape/dtype");
+  UmmaParams p;
+  p.bias = a.bias; p.out = a.out; p.res = a.res; p.accum = a.accum; p.scale = a.scale;
+  p.out_bf16 = a.out_dtype == BVG_BF16;
+  p.B = a.B; p.T = (int)a.T; p.Cin_p = a.Cin_p; p.Cout_n = a.Cout_n; p.out_ld = a.out_ld;
+  p.k = a.k; p.dil = a.dil; p.center = (a.k - 1) / 2;
+  p.KC = (a.Cin_p % 64 == 0) ? 64 : (a.Cin_p % 32 == 0 ? 32 : 16);
+  p.nchunks = a.Cin_p / p.KC;
+  p.NT = 256;
+  const bool per_tap = (variant & 2) != 0;
+  const int xrows = per_tap ? p.NT : p.NT + (a.k - 1) * a.dil;
+  p.x_box_rows = round_up((xrows + 1) / 2, 8);
+  if (2 * p.x_box_rows > UM_MAX_X_ROWS) BVG_FAIL(BVG_EINVAL, "conv_umma: halo too large");
+  p.n_ttiles = (int)ceil_div(a.T, p.NT);
+  p.n_cotiles = (int)ceil_div(a.Cout_n, UM_M);
+  p.n_tiles = (int64_t)a.B * p.n_ttiles * p.n_cotiles;
+  p.base_mode = variant & 1;
+
+  CUtensorMap mx, mw;
+  const int row_bytes = p.KC * 2;
+  int rc = make_map_3d(&mx, a.in, (uint64_t)a.Cin_p, (uint64_t)a.T, (uint64_t)a.B, (uint32_t)p.KC,
+                       (uint32_t)p.x_box_rows, row_bytes);
+  if (rc) return rc;
+  rc = make_map_3d(&mw, a.w, (uint64_t)a.Cin_p, (uint64_t)a.Cout_r, (uint64_t)a.k, (uint32_t)p.KC, UM_M, row_bytes);
+  if (rc) return rc;
+
+  if (g_sm_count == 0) {
+    int dev = 0;
+    BVG_CUDA(cudaGetDevice(&dev));
+    BVG_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+  BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
+  const unsigned grid = (unsigned)(p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count);
+  if (per_tap)
+    conv_umma_kernel<true><<<grid, UM_THREADS, UM_SMEM_BYTES, st>>>(mx, mw, p);
+  else
+    conv_umma_kernel<false><<<grid, UM_THREADS, UM_SMEM_BYTES, st>>>(mx, mw, p);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+}  // namespace bvg

@@ -1,0 +1,241 @@
+// Layout conversion and weight packing kernels.
+//
+// Internal activation layout: channels-last [B, T, Cp], Cp = channels padded to
+// a multiple of 16 (pad channels are always zero).  Internal conv weights:
+// Wp[tap][Cout_r][Cin_p] (input channel fastest), Cout_r = Cout padded to a
+// multiple of 128 - this is directly the K-major A operand of the tcgen05 kernel
+// and is also what the fp32 SIMT kernel reads.
+#include "common.cuh"
+
+namespace bvg {
+
+// [B, C, T] (time fastest) -> [B, T, Cp] (channel fastest), zero pad channels
+template <typename Tin, typename Tout>
+__global__ void bct_to_btc_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, int C, int Cp, int64_t T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const Tin* s = src + (int64_t)b * C * T;
+  Tout* d = dst + (int64_t)b * T * Cp;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? to_f32<Tin>(s[(int64_t)c * T + t]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t t = t0 + i;
+    const int c = c0 + threadIdx.x;
+    if (t < T && c < Cp) d[t * Cp + c] = from_f32<Tout>(tile[threadIdx.x][i]);
+  }
+}
+
+// [B, T, Cp] -> [B, C, T]
+template <typename Tin, typename Tout>
+__global__ void btc_to_bct_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, int C, int Cp, int64_t T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const Tin* s = src + (int64_t)b * T * Cp;
+  Tout* d = dst + (int64_t)b * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t t = t0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && c < Cp) ? to_f32<Tin>(s[t * Cp + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t t = t0 + threadIdx.x;
+    if (c < C && t < T) d[(int64_t)c * T + t] = from_f32<Tout>(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename Tin, typename Tout>
+static int launch_bct_to_btc(void* dst, const void* src, int B, int C, int Cp, int64_t T, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(T, 32), (unsigned)ceil_div(Cp, 32), (unsigned)B), block(32, 8);
+  bct_to_btc_kernel<Tin, Tout><<<grid, block, 0, st>>>((Tout*)dst, (const Tin*)src, C, Cp, T);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+template <typename Tin, typename Tout>
+static int launch_btc_to_bct(void* dst, const void* src, int B, int C, int Cp, int64_t T, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(T, 32), (unsigned)ceil_div(Cp, 32), (unsigned)B), block(32, 8);
+  btc_to_bct_kernel<Tin, Tout><<<grid, block, 0, st>>>((Tout*)dst, (const Tin*)src, C, Cp, T);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+int bct_to_btc(void* dst, int out_dtype, const float* src, int B, int C, int Cp, int64_t T, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return BVG_OK;
+  return out_dtype == BVG_BF16 ? launch_bct_to_btc<float, __nv_bfloat16>(dst, src, B, C, Cp, T, st)
+                               : launch_bct_to_btc<float, float>(dst, src, B, C, Cp, T, st);
+}
+int btc_to_bct(float* dst, const void* src, int in_dtype, int B, int C, int Cp, int64_t T, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return BVG_OK;
+  return in_dtype == BVG_BF16 ? launch_btc_to_bct<__nv_bfloat16, float>(dst, src, B, C, Cp, T, st)
+                              : launch_btc_to_bct<float, float>(dst, src, B, C, Cp, T, st);
+}
+
+// ---- weight packing -------------------------------------------------------------
+// Conv1d weight [Cout, Cin, k] (torch) -> Wp[k][Cout_r][Cin_p]
+template <typename Tout>
+__global__ void pack_conv_kernel(Tout* __restrict__ wp, const float* __restrict__ w, int Cout, int Cin, int k,
+                                 int Cout_r, int Cin_p) {
+  const int64_t n = (int64_t)k * Cout_r * Cin_p;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin_p);
+    const int co = (int)((i / Cin_p) % Cout_r);
+    const int j = (int)(i / ((int64_t)Cin_p * Cout_r));
+    float v = 0.f;
+    if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin + ci) * k + j];
+    wp[i] = from_f32<Tout>(v);
+  }
+}
+
+// ConvTranspose1d weight [Cin, Cout, 2u] (stride u, padding u/2) -> a 3-tap conv over
+// the INPUT time axis producing u*Cout_p "phase channels" per input sample:
+//   out[u*m + r, co] = sum_{tap in 0..2} Wp[tap][r*Cout_p + co][:] . x[m + tap - 1, :]
+// with, for s = r + u/2:  s <  u : tap1 <- W[:,:,s],   tap0 <- W[:,:,s+u]
+//                         s >= u : tap2 <- W[:,:,s-u], tap1 <- W[:,:,s]
+// (polyphase form of torch ConvTranspose1d)
+template <typename Tout>
+__global__ void pack_convtr_kernel(Tout* __restrict__ wp, const float* __restrict__ w, int Cin, int Cout, int u,
+                                   int Cout_p, int Cout_r, int Cin_p) {
+  const int k = 2 * u;
+  const int64_t n = (int64_t)3 * Cout_r * Cin_p;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin_p);
+    const int vc = (int)((i / Cin_p) % Cout_r);  // virtual output channel r*Cout_p + co
+    const int tap = (int)(i / ((int64_t)Cin_p * Cout_r));
+    float v = 0.f;
+    const int r = vc / Cout_p, co = vc % Cout_p;
+    if (ci < Cin && r < u && co < Cout) {
+      const int s = r + u / 2;
+      int widx = -1;
+      if (s < u) {
+        if (tap == 1) widx = s;
+        if (tap == 0) widx = s + u;
+      } else {
+        if (tap == 2) widx = s - u;
+        if (tap == 1) widx = s;
+      }
+      if (widx >= 0) v = w[((int64_t)ci * Cout + co) * k + widx];
+    }
+    wp[i] = from_f32<Tout>(v);
+  }
+}
+
+int pack_conv_weight(void* wp, int dtype, const float* w, int Cout, int Cin, int k, int Cout_r, int Cin_p,
+                     cudaStream_t st) {
+  const int64_t n = (int64_t)k * Cout_r * Cin_p;
+  const int blocks = (int)(ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096);
+  if (dtype == BVG_BF16)
+    pack_conv_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)wp, w, Cout, Cin, k, Cout_r, Cin_p);
+  else
+    pack_conv_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cout, Cin, k, Cout_r, Cin_p);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int Cout_p, int Cout_r,
+                       int Cin_p, cudaStream_t st) {
+  const int64_t n = (int64_t)3 * Cout_r * Cin_p;
+  const int blocks = (int)(ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096);
+  if (dtype == BVG_BF16)
+    pack_convtr_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)wp, w, Cin, Cout, u, Cout_p, Cout_r,
+                                                              Cin_p);
+  else
+    pack_convtr_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cin, Cout, u, Cout_p, Cout_r, Cin_p);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+// ---- conv_post (C -> 1, k = 7, pad 3) + clamp/tanh (+ optional int16) ------------------
+// reference: bigvgan.py:379-384 and infer_v2.py:740.  in: [B, T, Cp]; w: [7][Cp] fp32 (zero padded);
+// out: [B, 1, T] fp32 (or int16).  Memory-bound (reads Cp channels, writes 1).
+template <typename Tin, typename Tout>
+__global__ void conv_post_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ w,
+                                 float bias, int Cp, int64_t T, int use_tanh) {
+  extern __shared__ float sw[];  // [7][Cp]
+  for (int i = threadIdx.x; i < 7 * Cp; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const Tin* s = src + (int64_t)b * T * Cp;
+  float acc = bias;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int64_t tt = t + j - 3;
+    if (tt < 0 || tt >= T) continue;
+    const Tin* row = s + tt * Cp;
+    for (int c = 0; c < Cp; c += 8) {
+      float v[8];
+      if (sizeof(Tin) == 2) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row + c));
+        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[2 * q] = __uint_as_float(r[q] << 16);
+          v[2 * q + 1] = __uint_as_float(r[q] & 0xffff0000u);
+        }
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(row + c));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(row + c) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(sw[j * Cp + c + q], v[q], acc);
+    }
+  }
+  acc = use_tanh ? tanhf(acc) : fminf(fmaxf(acc, -1.0f), 1.0f);
+  if (sizeof(Tout) == 2) {
+    // clamp(32767 * wav, -32767, 32767) -> int16 (infer_v2.py:740; torch .type(int16) truncates)
+    float q = fminf(fmaxf(32767.0f * acc, -32767.0f), 32767.0f);
+    reinterpret_cast<int16_t*>(dst)[(int64_t)b * T + t] = (int16_t)q;
+  } else {
+    reinterpret_cast<float*>(dst)[(int64_t)b * T + t] = acc;
+  }
+}
+
+int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, const float* w, float bias, int B,
+                     int Cp, int64_t T, int use_tanh, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return BVG_OK;
+  dim3 grid((unsigned)ceil_div(T, 256), (unsigned)B);
+  const int smem = 7 * Cp * (int)sizeof(float);
+  if (in_dtype == BVG_BF16) {
+    if (out_i16)
+      conv_post_kernel<__nv_bfloat16, int16_t><<<grid, 256, smem, st>>>((int16_t*)dst, (const __nv_bfloat16*)src, w,
+                                                                        bias, Cp, T, use_tanh);
+    else
+      conv_post_kernel<__nv_bfloat16, float><<<grid, 256, smem, st>>>((float*)dst, (const __nv_bfloat16*)src, w,
+                                                                      bias, Cp, T, use_tanh);
+  } else {
+    if (out_i16)
+      conv_post_kernel<float, int16_t><<<grid, 256, smem, st>>>((int16_t*)dst, (const float*)src, w, bias, Cp, T,
+                                                                use_tanh);
+    else
+      conv_post_kernel<float, float><<<grid, 256, smem, st>>>((float*)dst, (const float*)src, w, bias, Cp, T,
+                                                              use_tanh);
+  }
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+// wav fp32 -> int16 (used when the int16 result is wanted from an fp32 wav buffer)
+__global__ void f32_to_i16_kernel(int16_t* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (int16_t)fminf(fmaxf(32767.0f * src[i], -32767.0f), 32767.0f);
+}
+int f32_to_i16(int16_t* dst, const float* src, int64_t n, cudaStream_t st) {
+  if (n <= 0) return BVG_OK;
+  const int blocks = (int)(ceil_div(n, 256) < 2048 ? ceil_div(n, 256) : 2048);
+  f32_to_i16_kernel<<<blocks, 256, 0, st>>>(dst, src, n);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+}  // namespace bvg

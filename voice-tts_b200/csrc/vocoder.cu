@@ -1,0 +1,614 @@
+// Whole-generator plan: weight ingestion (reference state-dict keys), workspace
+// arena, and the layer sequence of BigVGAN.forward (bigvgan.py:360-386) expressed
+// over the channels-last kernels of this library.  Host C++ only - no torch.
+//
+// Data flow per upsampling stage (bf16 mode; fp32 mode stores everything in fp32):
+//   X  (fp32) = ConvTranspose1d(prev)                      residual stream, shared by the 3 AMP blocks
+//   per AMP block j, per dilation layer l:
+//     A1 (bf16) = Activation1d(cur)                        cur = X (l == 0) or Y
+//     M  (bf16) = Conv1d(A1, dil = d_l) + bias
+//     A2 (bf16) = Activation1d(M)
+//     Y  (fp32) = Conv1d(A2) + bias + cur                  (l < last)
+//     XS (fp32) = (Conv1d(A2) + bias + cur) / nk [+ XS]    (l == last; the (xs0+xs1+xs2)/3 of bigvgan.py:369-375
+//                                                           folded into the epilogue; the last block of a stage
+//                                                           writes the next stage's bf16 ConvTranspose input)
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv.cuh"
+
+namespace bvg {
+
+struct ConvW {
+  void* w = nullptr;       // packed Wp[k][Cout_r][Cin_p]
+  float* bias = nullptr;   // [Cout_r]
+  int Cin = 0, Cout = 0, Cin_p = 0, Cout_p = 0, Cout_n = 0, Cout_r = 0;
+  int k = 0, k_torch = 0, dil = 1, up = 0;  // up > 0: ConvTranspose1d with stride `up`
+  bool has_w = false, has_b = false, want_b = true;
+};
+
+struct ActW {
+  float* alpha = nullptr;  // [Cp] log scale
+  float* beta = nullptr;   // [Cp] log scale
+  Taps taps;
+  int C = 0, Cp = 0;
+  bool has_a = false, has_b = false, has_up = false, has_down = false;
+};
+
+}  // namespace bvg
+
+using namespace bvg;
+
+struct bvg_vocoder {
+  bvg_config cfg;
+  int nst = 0, nk = 0, nd = 0;
+  int act_dt = BVG_BF16;          // storage type of conv operands
+  std::vector<int> C, Cp;         // C[0] = initial channels, C[i+1] = stage i
+  int mel_p = 0;
+  int total_up = 1;
+  ConvW conv_pre;
+  std::vector<ConvW> ups;
+  std::vector<ConvW> convs1, convs2;   // [(stage*nk + j)*nd + l]
+  std::vector<ActW> acts;              // [(stage*nk + j)*2*nd + a]
+  ActW act_post;
+  float* post_w = nullptr;             // [7][Cp_last]
+  float post_bias = 0.f;
+  bool has_post_w = false, has_post_b = false;
+  bool finalized = false;
+  // options
+  int opt_graph = 0, opt_conv_impl = 0, opt_umma_variant = 0, opt_fast_sin = -1;
+  int64_t opt_ws_cap_mb = 24 * 1024;
+  // workspace
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  float* pin_mel = nullptr; size_t pin_mel_bytes = 0;
+  void* pin_wav = nullptr;  size_t pin_wav_bytes = 0;
+  float* dev_mel = nullptr; size_t dev_mel_bytes = 0;
+  void* dev_wav = nullptr;  size_t dev_wav_bytes = 0;
+  int last_launches = 0;
+  std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int>> graphs;  // exec + kernels inside
+};
+
+namespace bvg {
+
+static int dev_alloc(void** p, size_t bytes) {
+  BVG_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  return BVG_OK;
+}
+
+static void init_conv(ConvW& c, int Cin, int Cout, int k, int dil, int up) {
+  c.Cin = Cin; c.Cout = Cout; c.k_torch = k; c.dil = dil; c.up = up;
+  c.Cin_p = pad_channels(Cin);
+  c.Cout_p = pad_channels(Cout);
+  if (up > 0) {
+    c.k = 3; c.dil = 1;
+    c.Cout_n = up * c.Cout_p;
+  } else {
+    c.k = k;
+    c.Cout_n = c.Cout_p;
+  }
+  c.Cout_r = round_up(c.Cout_n, 128);
+}
+
+static int alloc_conv(ConvW& c, int w_dt) {
+  int rc = dev_alloc(&c.w, (size_t)c.k * c.Cout_r * c.Cin_p * dtype_size(w_dt));
+  if (rc) return rc;
+  rc = dev_alloc((void**)&c.bias, (size_t)c.Cout_r * sizeof(float));
+  if (rc) return rc;
+  BVG_CUDA(cudaMemset(c.bias, 0, (size_t)c.Cout_r * sizeof(float)));
+  return BVG_OK;
+}
+
+static int alloc_act(ActW& a, int C) {
+  a.C = C; a.Cp = pad_channels(C);
+  int rc = dev_alloc((void**)&a.alpha, a.Cp * sizeof(float));
+  if (rc) return rc;
+  rc = dev_alloc((void**)&a.beta, a.Cp * sizeof(float));
+  if (rc) return rc;
+  BVG_CUDA(cudaMemset(a.alpha, 0, a.Cp * sizeof(float)));
+  BVG_CUDA(cudaMemset(a.beta, 0, a.Cp * sizeof(float)));
+  return BVG_OK;
+}
+
+struct Buffers {
+  void *mel, *p0, *nx, *a1, *m, *a2;
+  float *x, *y, *xs;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// workspace layout for a micro-batch of B utterances of T0 frames
+static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
+  const size_t es = dtype_size(v->act_dt);
+  size_t nmax = 0;
+  int64_t T = T0;
+  for (int i = 0; i < v->nst; ++i) {
+    T *= v->cfg.upsample_rates[i];
+    const size_t n = (size_t)B * T * v->Cp[i + 1];
+    if (n > nmax) nmax = n;
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t o_mel = take((size_t)B * T0 * v->mel_p * es);
+  const size_t o_p0 = take((size_t)B * T0 * v->Cp[0] * es);
+  const size_t o_nx = take(nmax * es);
+  const size_t o_a1 = take(nmax * es);
+  const size_t o_m = take(nmax * es);
+  const size_t o_a2 = take(nmax * es);
+  const size_t o_x = take(nmax * 4);
+  const size_t o_y = take(nmax * 4);
+  const size_t o_xs = take(nmax * 4);
+  if (out) {
+    unsigned char* base = (unsigned char*)v->arena;
+    out->mel = base + o_mel; out->p0 = base + o_p0; out->nx = base + o_nx;
+    out->a1 = base + o_a1; out->m = base + o_m; out->a2 = base + o_a2;
+    out->x = (float*)(base + o_x); out->y = (float*)(base + o_y); out->xs = (float*)(base + o_xs);
+  }
+  return off;
+}
+
+static int max_microbatch(const bvg_vocoder* v, int B, int T0) {
+  const size_t cap = (size_t)v->opt_ws_cap_mb << 20;
+  int b = B;
+  while (b > 1 && plan_buffers(v, b, T0, nullptr) > cap) b = (b + 1) / 2;
+  return b;
+}
+
+static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, void* out, int out_dt,
+                    const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st) {
+  ConvArgs a;
+  a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = res; a.accum = accum; a.scale = scale;
+  a.in_dtype = in_dt; a.w_dtype = v->act_dt; a.out_dtype = out_dt;
+  a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
+  a.k = c.k; a.dil = c.dil;
+  bool umma = (v->cfg.mode == BVG_MODE_BF16) && v->opt_conv_impl != 1;
+  if (umma && !conv_umma_supported(a)) {
+    if (v->opt_conv_impl == 2) BVG_FAIL(BVG_EINVAL, "conv layer not supported by the tcgen05 kernel");
+    umma = false;
+  }
+  return umma ? conv_umma_launch(a, v->opt_umma_variant, st) : conv_simt_launch(a, st);
+}
+
+static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, void* out, int out_dt, int B,
+                   int64_t T, cudaStream_t st) {
+  const bool fast = v->opt_fast_sin >= 0 ? v->opt_fast_sin != 0 : v->cfg.mode == BVG_MODE_BF16;
+  return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, a.Cp, in_dt, out_dt, fast, st);
+}
+
+// the layer sequence between the mel transpose and conv_post (graph-capturable)
+static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream_t st) {
+  const int adt = v->act_dt;
+  int rc = run_conv(v, v->conv_pre, bf.mel, adt, bf.p0, adt, nullptr, nullptr, 1.f, B, T0, st);
+  if (rc) return rc;
+  const void* stage_in = bf.p0;
+  int64_t T = T0;
+  for (int i = 0; i < v->nst; ++i) {
+    // ConvTranspose1d: 3-tap conv over the input rows writing u*Cp phase channels == [B, u*T, Cp]
+    rc = run_conv(v, v->ups[i], stage_in, adt, bf.x, BVG_F32, nullptr, nullptr, 1.f, B, T, st);
+    if (rc) return rc;
+    T *= v->cfg.upsample_rates[i];
+    const bool last_stage = (i == v->nst - 1);
+    for (int j = 0; j < v->nk; ++j) {
+      const float* cur = bf.x;
+      for (int l = 0; l < v->nd; ++l) {
+        const int ci = (i * v->nk + j) * v->nd + l;
+        const int ai = (i * v->nk + j) * 2 * v->nd + 2 * l;
+        rc = run_act(v, v->acts[ai], cur, BVG_F32, bf.a1, adt, B, T, st);
+        if (rc) return rc;
+        rc = run_conv(v, v->convs1[ci], bf.a1, adt, bf.m, adt, nullptr, nullptr, 1.f, B, T, st);
+        if (rc) return rc;
+        rc = run_act(v, v->acts[ai + 1], bf.m, adt, bf.a2, adt, B, T, st);
+        if (rc) return rc;
+        if (l < v->nd - 1) {
+          rc = run_conv(v, v->convs2[ci], bf.a2, adt, bf.y, BVG_F32, cur, nullptr, 1.f, B, T, st);
+          cur = bf.y;
+        } else {
+          const bool to_next = (j == v->nk - 1) && !last_stage;
+          rc = run_conv(v, v->convs2[ci], bf.a2, adt, to_next ? bf.nx : (void*)bf.xs, to_next ? adt : BVG_F32, cur,
+                        j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, st);
+        }
+        if (rc) return rc;
+      }
+    }
+    stage_in = bf.nx;
+  }
+  return run_act(v, v->act_post, bf.xs, BVG_F32, bf.a1, adt, B, T, st);
+}
+
+static int forward_chunk(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, int B, int T0,
+                         cudaStream_t st) {
+  Buffers bf;
+  plan_buffers(v, B, T0, &bf);
+  int rc = bct_to_btc(bf.mel, v->act_dt, mel, B, v->cfg.num_mels, v->mel_p, T0, st);
+  if (rc) return rc;
+  if (v->opt_graph) {
+    auto key = std::make_pair(B, T0);
+    auto it = v->graphs.find(key);
+    if (it == v->graphs.end()) {
+      cudaGraph_t g = nullptr;
+      cudaStream_t cs;
+      BVG_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      BVG_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const uint64_t k0 = g_launches.load();
+      rc = run_body(v, bf, B, T0, cs);
+      const int nkern = (int)(g_launches.load() - k0);
+      g_launches.store(k0);  // captured, not launched
+      cudaError_t e = cudaStreamEndCapture(cs, &g);
+      cudaStreamDestroy(cs);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      BVG_CUDA(e);
+      cudaGraphExec_t ge = nullptr;
+      BVG_CUDA(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      it = v->graphs.emplace(key, std::make_pair(ge, nkern)).first;
+    }
+    BVG_CUDA(cudaGraphLaunch(it->second.first, st));
+    g_launches.fetch_add((uint64_t)it->second.second);
+  } else {
+    rc = run_body(v, bf, B, T0, st);
+    if (rc) return rc;
+  }
+  const int64_t Tw = (int64_t)T0 * v->total_up;
+  return conv_post_launch(wav, wav_i16, bf.a1, v->act_dt, v->post_w, v->post_bias, B, v->Cp[v->nst], Tw,
+                          v->cfg.use_tanh_at_final, st);
+}
+
+static int ensure_arena(bvg_vocoder* v, size_t need) {
+  if (need <= v->arena_bytes) return BVG_OK;
+  // graphs bake arena addresses
+  for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
+  v->graphs.clear();
+  if (v->arena) {
+    BVG_CUDA(cudaDeviceSynchronize());
+    cudaFree(v->arena);
+    v->arena = nullptr;
+    v->arena_bytes = 0;
+  }
+  BVG_CUDA(cudaMalloc(&v->arena, need));
+  v->arena_bytes = need;
+  return BVG_OK;
+}
+
+int vocoder_forward(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, int B, int T0, cudaStream_t st) {
+  if (!v || !v->finalized) BVG_FAIL(BVG_ESTATE, "vocoder handle is not finalized");
+  if (B < 0 || T0 < 0) BVG_FAIL(BVG_EINVAL, "negative batch or length");
+  if (B == 0 || T0 == 0) return BVG_OK;
+  if (!mel || !wav) BVG_FAIL(BVG_EINVAL, "null mel/wav pointer");
+  if ((int64_t)T0 * v->total_up > 0x3fffffffLL) BVG_FAIL(BVG_EINVAL, "utterance too long");
+  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  const uint64_t l0 = g_launches.load();
+  const int mb = max_microbatch(v, B, T0);
+  rc = ensure_arena(v, plan_buffers(v, mb, T0, nullptr));
+  if (rc) return rc;
+  const int64_t Tw = (int64_t)T0 * v->total_up;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int bc = (B - b0 < mb) ? B - b0 : mb;
+    void* wv = wav_i16 ? (void*)((int16_t*)wav + (int64_t)b0 * Tw) : (void*)((float*)wav + (int64_t)b0 * Tw);
+    rc = forward_chunk(v, mel + (int64_t)b0 * v->cfg.num_mels * T0, wv, wav_i16, bc, T0, st);
+    if (rc) return rc;
+  }
+  v->last_launches = (int)(g_launches.load() - l0);
+  return BVG_OK;
+}
+
+// ------------------------------------------------------------------ weights ----
+static bool parse_int(const char*& s, int* out) {
+  if (*s < '0' || *s > '9') return false;
+  int v = 0;
+  while (*s >= '0' && *s <= '9') v = v * 10 + (*s++ - '0');
+  *out = v;
+  return true;
+}
+static bool eat(const char*& s, const char* lit) {
+  size_t n = strlen(lit);
+  if (strncmp(s, lit, n) != 0) return false;
+  s += n;
+  return true;
+}
+
+static int set_conv_tensor(bvg_vocoder* v, ConvW& c, bool is_weight, const float* d_data, int64_t numel,
+                           const char* name) {
+  if (is_weight) {
+    const int64_t want = (int64_t)c.Cin * c.Cout * c.k_torch;
+    if (numel != want) BVG_FAIL(BVG_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)want, (long long)numel);
+    int rc = c.up > 0 ? pack_convtr_weight(c.w, v->act_dt, d_data, c.Cin, c.Cout, c.up, c.Cout_p, c.Cout_r, c.Cin_p, 0)
+                      : pack_conv_weight(c.w, v->act_dt, d_data, c.Cout, c.Cin, c.k, c.Cout_r, c.Cin_p, 0);
+    if (rc) return rc;
+    c.has_w = true;
+  } else {
+    if (numel != c.Cout) BVG_FAIL(BVG_EINVAL, "%s: expected %d elements, got %lld", name, c.Cout, (long long)numel);
+    if (c.up > 0) {
+      for (int r = 0; r < c.up; ++r)
+        BVG_CUDA(cudaMemcpy(c.bias + (size_t)r * c.Cout_p, d_data, c.Cout * sizeof(float), cudaMemcpyDeviceToDevice));
+    } else {
+      BVG_CUDA(cudaMemcpy(c.bias, d_data, c.Cout * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    c.has_b = true;
+  }
+  return BVG_OK;
+}
+
+static int set_act_tensor(bvg_vocoder* v, ActW& a, const char* field, const float* d_data, int64_t numel,
+                          const char* name) {
+  if (!strcmp(field, "act.alpha") || !strcmp(field, "act.beta")) {
+    if (numel != a.C) BVG_FAIL(BVG_EINVAL, "%s: expected %d elements, got %lld", name, a.C, (long long)numel);
+    std::vector<float> h(a.C);
+    BVG_CUDA(cudaMemcpy(h.data(), d_data, a.C * sizeof(float), cudaMemcpyDeviceToHost));
+    if (!v->cfg.snake_logscale)
+      for (auto& x : h) x = logf(x);  // the kernels apply exp (as the reference's fused kernel, cuda/activation1d.py:68-72)
+    const bool is_alpha = !strcmp(field, "act.alpha");
+    if (is_alpha) {
+      BVG_CUDA(cudaMemcpy(a.alpha, h.data(), a.C * sizeof(float), cudaMemcpyHostToDevice));
+      a.has_a = true;
+      if (v->cfg.snake_kind == BVG_SNAKE) {  // Snake: beta == alpha (cuda/activation1d.py:61-62)
+        BVG_CUDA(cudaMemcpy(a.beta, h.data(), a.C * sizeof(float), cudaMemcpyHostToDevice));
+        a.has_b = true;
+      }
+    } else {
+      if (v->cfg.snake_kind == BVG_SNAKE) BVG_FAIL(BVG_EINVAL, "%s: Snake has no beta", name);
+      BVG_CUDA(cudaMemcpy(a.beta, h.data(), a.C * sizeof(float), cudaMemcpyHostToDevice));
+      a.has_b = true;
+    }
+    return BVG_OK;
+  }
+  const bool up = !strcmp(field, "upsample.filter");
+  const bool down = !strcmp(field, "downsample.lowpass.filter");
+  if (up || down) {
+    if (numel != 12) BVG_FAIL(BVG_EINVAL, "%s: only 12-tap filters are supported (got %lld)", name, (long long)numel);
+    float h[12];
+    BVG_CUDA(cudaMemcpy(h, d_data, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 12; ++i) {
+      if (up) a.taps.up[i] = 2.0f * h[i];  // the x2 zero-stuffing gain of UpSample1d (resample.py:33), exact in fp
+      else a.taps.down[i] = h[i];
+    }
+    (up ? a.has_up : a.has_down) = true;
+    return BVG_OK;
+  }
+  BVG_FAIL(BVG_EINVAL, "unknown tensor name '%s'", name);
+}
+
+int vocoder_set_tensor(bvg_vocoder* v, const char* name, const float* data, int64_t numel, int is_device) {
+  if (!v || !name || !data || numel <= 0) BVG_FAIL(BVG_EINVAL, "bvg_set_tensor: bad argument");
+  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  float* tmp = nullptr;
+  const float* d = data;
+  if (!is_device) {
+    BVG_CUDA(cudaMalloc((void**)&tmp, numel * sizeof(float)));
+    cudaError_t e = cudaMemcpy(tmp, data, numel * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(tmp); BVG_CUDA(e); }
+    d = tmp;
+  }
+  int rc = BVG_OK;
+  const char* s = name;
+  int n = 0, l = 0;
+  if (eat(s, "conv_pre.")) {
+    rc = !strcmp(s, "weight") ? set_conv_tensor(v, v->conv_pre, true, d, numel, name)
+         : !strcmp(s, "bias") ? set_conv_tensor(v, v->conv_pre, false, d, numel, name)
+                              : (set_error("unknown tensor name '%s'", name), BVG_EINVAL);
+  } else if (eat(s, "ups.")) {
+    if (!parse_int(s, &n) || n >= v->nst || !eat(s, ".0.")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+    else rc = !strcmp(s, "weight") ? set_conv_tensor(v, v->ups[n], true, d, numel, name)
+              : !strcmp(s, "bias") ? set_conv_tensor(v, v->ups[n], false, d, numel, name)
+                                   : (set_error("unknown tensor name '%s'", name), BVG_EINVAL);
+  } else if (eat(s, "resblocks.")) {
+    if (!parse_int(s, &n) || n >= v->nst * v->nk || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+    else if (eat(s, "convs1.") || (s[5] == '2' && eat(s, "convs2."))) {
+      const bool second = s[-2] == '2';
+      if (!parse_int(s, &l) || l >= v->nd || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+      else {
+        ConvW& c = (second ? v->convs2 : v->convs1)[n * v->nd + l];
+        rc = !strcmp(s, "weight") ? set_conv_tensor(v, c, true, d, numel, name)
+             : !strcmp(s, "bias") ? set_conv_tensor(v, c, false, d, numel, name)
+                                  : (set_error("unknown tensor name '%s'", name), BVG_EINVAL);
+      }
+    } else if (eat(s, "activations.")) {
+      if (!parse_int(s, &l) || l >= 2 * v->nd || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+      else rc = set_act_tensor(v, v->acts[n * 2 * v->nd + l], s, d, numel, name);
+    } else { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+  } else if (eat(s, "activation_post.")) {
+    rc = set_act_tensor(v, v->act_post, s, d, numel, name);
+  } else if (eat(s, "conv_post.")) {
+    const int Cl = v->C[v->nst], Clp = v->Cp[v->nst];
+    if (!strcmp(s, "weight")) {
+      if (numel != (int64_t)Cl * 7) { set_error("%s: expected %d elements", name, Cl * 7); rc = BVG_EINVAL; }
+      else {
+        std::vector<float> h(Cl * 7), pk(7 * Clp, 0.f);
+        cudaError_t e = cudaMemcpy(h.data(), d, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) {
+          for (int c = 0; c < Cl; ++c)
+            for (int j = 0; j < 7; ++j) pk[j * Clp + c] = h[c * 7 + j];  // weight [1, C, 7]
+          e = cudaMemcpy(v->post_w, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice);
+        }
+        if (e != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; }
+        else v->has_post_w = true;
+      }
+    } else if (!strcmp(s, "bias")) {
+      if (!v->cfg.use_bias_at_final || numel != 1) { set_error("%s: unexpected conv_post.bias", name); rc = BVG_EINVAL; }
+      else {
+        cudaError_t e = cudaMemcpy(&v->post_bias, d, sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; }
+        else v->has_post_b = true;
+      }
+    } else { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+  } else {
+    set_error("unknown tensor name '%s'", name);
+    rc = BVG_EINVAL;
+  }
+  cudaError_t e = cudaDeviceSynchronize();  // packing kernels read `data`; the caller may free it on return
+  if (tmp) cudaFree(tmp);
+  if (rc == BVG_OK && e != cudaSuccess) { set_error("weight packing failed: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; }
+  return rc;
+}
+
+int vocoder_create(const bvg_config* cfg, bvg_vocoder** out) {
+  if (!cfg || !out) BVG_FAIL(BVG_EINVAL, "bvg_create: null argument");
+  *out = nullptr;
+  if (cfg->num_upsamples < 1 || cfg->num_upsamples > 8 || cfg->num_kernels < 1 || cfg->num_kernels > 4 ||
+      cfg->num_dilations < 1 || cfg->num_dilations > 4 || cfg->num_mels < 1 || cfg->upsample_initial_channel < 2)
+    BVG_FAIL(BVG_EINVAL, "bvg_create: configuration out of range");
+  if (cfg->mode != BVG_MODE_FP32 && cfg->mode != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_create: unknown mode %d", cfg->mode);
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    const int u = cfg->upsample_rates[i];
+    if (u < 2 || u % 2 != 0 || cfg->upsample_kernel_sizes[i] != 2 * u)
+      BVG_FAIL(BVG_EINVAL, "bvg_create: upsample stage %d needs even rate u and kernel 2u (got u=%d k=%d)", i, u,
+               cfg->upsample_kernel_sizes[i]);
+    if ((cfg->upsample_initial_channel >> (i + 1)) < 1) BVG_FAIL(BVG_EINVAL, "bvg_create: too many stages for the channel count");
+  }
+  for (int j = 0; j < cfg->num_kernels; ++j) {
+    if (cfg->resblock_kernel_sizes[j] % 2 != 1) BVG_FAIL(BVG_EINVAL, "bvg_create: resblock kernels must be odd");
+    for (int l = 0; l < cfg->num_dilations; ++l)
+      if (cfg->resblock_dilations[j][l] < 1) BVG_FAIL(BVG_EINVAL, "bvg_create: bad dilation");
+  }
+  BVG_CUDA(cudaSetDevice(cfg->device));
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+
+  bvg_vocoder* v = new (std::nothrow) bvg_vocoder();
+  if (!v) BVG_FAIL(BVG_ENOMEM, "out of host memory");
+  v->cfg = *cfg;
+  v->nst = cfg->num_upsamples; v->nk = cfg->num_kernels; v->nd = cfg->num_dilations;
+  v->act_dt = cfg->mode == BVG_MODE_BF16 ? BVG_BF16 : BVG_F32;
+  v->mel_p = pad_channels(cfg->num_mels);
+  v->C.resize(v->nst + 1); v->Cp.resize(v->nst + 1);
+  v->C[0] = cfg->upsample_initial_channel;
+  for (int i = 0; i < v->nst; ++i) { v->C[i + 1] = cfg->upsample_initial_channel >> (i + 1); v->total_up *= cfg->upsample_rates[i]; }
+  for (int i = 0; i <= v->nst; ++i) v->Cp[i] = pad_channels(v->C[i]);
+  for (int i = 0; i < 12; ++i) { v->act_post.taps.up[i] = 0.f; v->act_post.taps.down[i] = 0.f; }
+
+#define TRY(x) do { rc = (x); if (rc) { bvg_destroy(v); return rc; } } while (0)
+  init_conv(v->conv_pre, cfg->num_mels, v->C[0], 7, 1, 0);
+  TRY(alloc_conv(v->conv_pre, v->act_dt));
+  v->ups.resize(v->nst);
+  for (int i = 0; i < v->nst; ++i) {
+    init_conv(v->ups[i], v->C[i], v->C[i + 1], cfg->upsample_kernel_sizes[i], 1, cfg->upsample_rates[i]);
+    TRY(alloc_conv(v->ups[i], v->act_dt));
+  }
+  v->convs1.resize(v->nst * v->nk * v->nd); v->convs2.resize(v->nst * v->nk * v->nd);
+  v->acts.resize(v->nst * v->nk * 2 * v->nd);
+  for (int i = 0; i < v->nst; ++i)
+    for (int j = 0; j < v->nk; ++j)
+      for (int l = 0; l < v->nd; ++l) {
+        const int ci = (i * v->nk + j) * v->nd + l;
+        init_conv(v->convs1[ci], v->C[i + 1], v->C[i + 1], cfg->resblock_kernel_sizes[j], cfg->resblock_dilations[j][l], 0);
+        init_conv(v->convs2[ci], v->C[i + 1], v->C[i + 1], cfg->resblock_kernel_sizes[j], 1, 0);
+        TRY(alloc_conv(v->convs1[ci], v->act_dt));
+        TRY(alloc_conv(v->convs2[ci], v->act_dt));
+        for (int a = 0; a < 2; ++a) TRY(alloc_act(v->acts[(i * v->nk + j) * 2 * v->nd + 2 * l + a], v->C[i + 1]));
+      }
+  TRY(alloc_act(v->act_post, v->C[v->nst]));
+  TRY(dev_alloc((void**)&v->post_w, 7 * v->Cp[v->nst] * sizeof(float)));
+#undef TRY
+  *out = v;
+  return BVG_OK;
+}
+
+int vocoder_finalize(bvg_vocoder* v) {
+  if (!v) BVG_FAIL(BVG_EINVAL, "null handle");
+  auto chk_conv = [&](const ConvW& c, const char* what, int idx, bool need_bias) -> int {
+    if (!c.has_w) BVG_FAIL(BVG_ESTATE, "missing weight: %s[%d].weight", what, idx);
+    if (need_bias && !c.has_b) BVG_FAIL(BVG_ESTATE, "missing weight: %s[%d].bias", what, idx);
+    return BVG_OK;
+  };
+  auto chk_act = [&](const ActW& a, const char* what, int idx) -> int {
+    if (!a.has_a || !a.has_b) BVG_FAIL(BVG_ESTATE, "missing snake parameters: %s[%d]", what, idx);
+    if (!a.has_up || !a.has_down) BVG_FAIL(BVG_ESTATE, "missing filter taps: %s[%d]", what, idx);
+    return BVG_OK;
+  };
+  int rc;
+  if ((rc = chk_conv(v->conv_pre, "conv_pre", 0, true))) return rc;
+  for (int i = 0; i < v->nst; ++i) if ((rc = chk_conv(v->ups[i], "ups", i, true))) return rc;
+  for (size_t i = 0; i < v->convs1.size(); ++i) {
+    if ((rc = chk_conv(v->convs1[i], "convs1", (int)i, true))) return rc;
+    if ((rc = chk_conv(v->convs2[i], "convs2", (int)i, true))) return rc;
+  }
+  for (size_t i = 0; i < v->acts.size(); ++i) if ((rc = chk_act(v->acts[i], "activations", (int)i))) return rc;
+  if ((rc = chk_act(v->act_post, "activation_post", 0))) return rc;
+  if (!v->has_post_w) BVG_FAIL(BVG_ESTATE, "missing weight: conv_post.weight");
+  if (v->cfg.use_bias_at_final && !v->has_post_b) BVG_FAIL(BVG_ESTATE, "missing weight: conv_post.bias");
+  v->finalized = true;
+  return BVG_OK;
+}
+
+int64_t vocoder_workspace_bytes(const bvg_vocoder* v, int B, int T0) {
+  if (!v || B <= 0 || T0 <= 0) return 0;
+  return (int64_t)plan_buffers(v, max_microbatch(v, B, T0), T0, nullptr);
+}
+
+int vocoder_forward_host(bvg_vocoder* v, const float* mel_host, void* wav_host, int wav_dtype, int B, int T0,
+                         cudaStream_t st) {
+  if (!v || !v->finalized) BVG_FAIL(BVG_ESTATE, "vocoder handle is not finalized");
+  if (B == 0 || T0 == 0) return BVG_OK;
+  if (B < 0 || T0 < 0 || !mel_host || !wav_host) BVG_FAIL(BVG_EINVAL, "bad argument");
+  if (wav_dtype != 0 && wav_dtype != 1) BVG_FAIL(BVG_EDTYPE, "wav_dtype must be 0 (fp32) or 1 (int16)");
+  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  const size_t mel_bytes = (size_t)B * v->cfg.num_mels * T0 * sizeof(float);
+  const int64_t nw = (int64_t)B * T0 * v->total_up;
+  const size_t wav_bytes = (size_t)nw * (wav_dtype ? 2 : 4);
+  if (mel_bytes > v->pin_mel_bytes) {
+    if (v->pin_mel) cudaFreeHost(v->pin_mel);
+    if (v->dev_mel) cudaFree(v->dev_mel);
+    v->pin_mel = nullptr; v->dev_mel = nullptr; v->pin_mel_bytes = 0;
+    BVG_CUDA(cudaMallocHost((void**)&v->pin_mel, mel_bytes));
+    BVG_CUDA(cudaMalloc((void**)&v->dev_mel, mel_bytes));
+    v->pin_mel_bytes = mel_bytes;
+  }
+  if (wav_bytes > v->pin_wav_bytes) {
+    if (v->pin_wav) cudaFreeHost(v->pin_wav);
+    if (v->dev_wav) cudaFree(v->dev_wav);
+    v->pin_wav = nullptr; v->dev_wav = nullptr; v->pin_wav_bytes = 0;
+    BVG_CUDA(cudaMallocHost(&v->pin_wav, wav_bytes));
+    BVG_CUDA(cudaMalloc(&v->dev_wav, wav_bytes));
+    v->pin_wav_bytes = wav_bytes;
+  }
+  memcpy(v->pin_mel, mel_host, mel_bytes);
+  BVG_CUDA(cudaMemcpyAsync(v->dev_mel, v->pin_mel, mel_bytes, cudaMemcpyHostToDevice, st));
+  int rc = vocoder_forward(v, v->dev_mel, v->dev_wav, wav_dtype, B, T0, st);
+  if (rc) return rc;
+  BVG_CUDA(cudaMemcpyAsync(v->pin_wav, v->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, st));
+  BVG_CUDA(cudaStreamSynchronize(st));
+  memcpy(wav_host, v->pin_wav, wav_bytes);
+  return BVG_OK;
+}
+
+}  // namespace bvg
+
+extern "C" void bvg_destroy(bvg_vocoder* v) {
+  if (!v) return;
+  cudaSetDevice(v->cfg.device);
+  cudaDeviceSynchronize();
+  auto free_conv = [](ConvW& c) { if (c.w) cudaFree(c.w); if (c.bias) cudaFree(c.bias); };
+  auto free_act = [](ActW& a) { if (a.alpha) cudaFree(a.alpha); if (a.beta) cudaFree(a.beta); };
+  free_conv(v->conv_pre);
+  for (auto& c : v->ups) free_conv(c);
+  for (auto& c : v->convs1) free_conv(c);
+  for (auto& c : v->convs2) free_conv(c);
+  for (auto& a : v->acts) free_act(a);
+  free_act(v->act_post);
+  if (v->post_w) cudaFree(v->post_w);
+  for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
+  if (v->arena) cudaFree(v->arena);
+  if (v->pin_mel) cudaFreeHost(v->pin_mel);
+  if (v->pin_wav) cudaFreeHost(v->pin_wav);
+  if (v->dev_mel) cudaFree(v->dev_mel);
+  if (v->dev_wav) cudaFree(v->dev_wav);
+  delete v;
+}
+
+extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
+  if (!v || !key) BVG_FAIL(BVG_EINVAL, "bvg_set_option: null argument");
+  if (!strcmp(key, "graph")) v->opt_graph = value;
+  else if (!strcmp(key, "conv_impl")) v->opt_conv_impl = value;
+  else if (!strcmp(key, "umma_variant")) v->opt_umma_variant = value;
+  else if (!strcmp(key, "fast_sin")) v->opt_fast_sin = value;
+  else if (!strcmp(key, "workspace_mb")) v->opt_ws_cap_mb = value;
+  else BVG_FAIL(BVG_EINVAL, "bvg_set_option: unknown option '%s'", key);
+  return BVG_OK;
+}
+
+extern "C" int bvg_last_forward_launches(const bvg_vocoder* v) { return v ? v->last_launches : 0; }
