@@ -1,0 +1,88 @@
+"""GPU parity of the dense layers: fp32 SIMT mode and the bf16 tcgen05 mode."""
+import pytest
+import torch
+
+from oracle import bigvgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import importlib
+    return importlib.import_module("voice-tts_b200.ops")
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+CONV_CASES = [  # B, Cin, Cout, T, k, dil
+    (1, 16, 16, 50, 3, 1), (2, 24, 24, 300, 11, 5), (1, 80, 200, 64, 7, 1), (1, 12, 12, 77, 7, 3),
+    (1, 96, 96, 1000, 7, 3), (2, 48, 48, 513, 3, 5), (1, 192, 192, 256, 11, 1), (1, 1, 5, 9, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv1d(ops, case, precision):
+    B, Cin, Cout, T, k, d = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    if precision == "bf16":   # bf16 operands, fp32 accumulate: exact w.r.t. the rounded operands
+        x, w = bf(x), bf(w)
+    ref = O.conv1d(x.double(), w.double(), b.double(), d)
+    y = ops.conv1d(x.to(DEV), w.to(DEV), b.to(DEV), d, precision, 0).cpu().double()
+    assert (y - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+    ref2 = O.conv1d_indexed(x.double(), w.double(), b.double(), d)
+    assert (ref - ref2).abs().max() < 1e-10
+
+
+@pytest.mark.parametrize("case", [(1, 32, 16, 40, 4), (2, 48, 24, 33, 2), (1, 256, 128, 300, 4), (1, 24, 12, 50, 2)],
+                         ids=str)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_transpose1d(ops, case, precision):
+    B, Cin, Cout, T, u = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, 2 * u, generator=g) / (Cin * 2) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    if precision == "bf16":
+        x, w = bf(x), bf(w)
+    ref = O.conv_transpose1d(x.double(), w.double(), b.double(), u)
+    y = ops.conv_transpose1d(x.to(DEV), w.to(DEV), b.to(DEV), u, precision, 0).cpu().double()
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+
+
+def test_conv1d_full_size_tcgen05(ops):
+    """the largest real layer (768ch, k=11, d=5) at 16 x 10 s would be 1.7 TFLOP for the
+    CPU oracle; check one utterance slice against the oracle and the rest through
+    batch independence + linearity."""
+    g = torch.Generator().manual_seed(0)
+    B, C, T, k, d = 4, 768, 3444, 11, 5
+    x = bf(torch.randn(B, C, T, generator=g))
+    w = bf(torch.randn(C, C, k, generator=g) / (C * k) ** 0.5)
+    b = torch.randn(C, generator=g)
+    y = ops.conv1d(x.to(DEV), w.to(DEV), b.to(DEV), d, "bf16", 0)
+    ref = O.conv1d(x[1:2, :, 1000:1400], w, b, d)[:, :, 30:-30]
+    got = y[1:2, :, 1030:1370].cpu()
+    assert (got - ref).abs().max() <= 2e-5 * float(ref.abs().max())
+    y1 = ops.conv1d(x[2:3].contiguous().to(DEV), w.to(DEV), b.to(DEV), d, "bf16", 0)
+    assert torch.equal(y1, y[2:3])
+    # fp32 SIMT and tcgen05 agree on identical (bf16-representable) operands
+    ys = ops.conv1d(x[:1].contiguous().to(DEV), w.to(DEV), b.to(DEV), d, "fp32", 0)
+    assert (ys - y[:1]).abs().max() <= 2e-5 * float(ys.abs().max())
+
+
+def test_conv_errors(ops):
+    x = torch.zeros(1, 4, 8, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.conv1d(x, torch.zeros(4, 4, 4, device=DEV), torch.zeros(4, device=DEV), 1, "fp32", 0)   # even k
+    with pytest.raises(RuntimeError):
+        ops.conv1d(x, torch.zeros(4, 4, 3, device=DEV), torch.zeros(4, device=DEV), 1, "fp16", 0)
+    with pytest.raises(RuntimeError):
+        ops.conv_transpose1d(x, torch.zeros(4, 2, 6, device=DEV), torch.zeros(2, device=DEV), 2, "fp32", 0)  # k != 2u

@@ -150,6 +150,7 @@ static int launch_bct(void* dst, const void* src, const float* alpha_log, const 
   const int64_t per_tile = ceil_div(Tlen, tiles_per_row);
   int L = (int)ceil_div(per_tile, kBctThreads);
   if (L % 2 == 0) L += 1;           // odd stride => conflict-free shared-memory walk
+  if (L < 3) L = 3;                 // only the first segment of a row may see v[m<0] (needs 2*L-5 >= 0)
   if (L > kBctMaxSeg) L = kBctMaxSeg;
   const int tile_len = kBctThreads * L;   // multiple of 128 elements
   const int64_t blocks = rows * tiles_per_row;
@@ -159,12 +160,8 @@ static int launch_bct(void* dst, const void* src, const float* alpha_log, const 
   const int in_bytes = ((tile_len + 2 * kBctHalo) * (int)sizeof(T) + 127) & ~127;
   const int smem = in_bytes + tile_len * (int)sizeof(T);
   auto kern = act1d_bct_kernel<T, FAST>;
-  static bool attr_done = false;  // per template instantiation
-  if (!attr_done) {
-    const int max_smem = (((max_tile + 2 * kBctHalo) * (int)sizeof(T) + 127) & ~127) + max_tile * (int)sizeof(T);
-    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_done = true;
-  }
+  if (smem > 48 * 1024)  // per device/context attribute; cheap enough to set on every large launch
+    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<(unsigned)blocks, kBctThreads, smem, st>>>((T*)dst, (const T*)src, alpha_log, beta_log, taps, C,
                                                     Tlen, L, tile_len, tiles_per_row, aligned);
   BVG_LAUNCHED();
