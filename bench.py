@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the BigVGAN v2 vocoder hot path on B200 (see DESIGN.md, section Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the generator over one batch of synthetic mels (the
+BASELINE configs[1] workload: 16 utterances x 10 s per GPU, bf16 tensor-core
+mode).  Rank 0 prints ONE JSON line.  `value` = audio-seconds generated per
+wall-second over all ranks with the mels already resident in HBM; `e2e` = the
+same through the host-buffer C-ABI call (`bvg_vocoder_fwd_host`: pinned H2D of
+the mels + generator + D2H of the waveform inside the timed region).
+
+`--impl reference` times the reference algorithm on the host cores (the oracle
+port of the reference's torch path - the Python reference itself cannot travel
+to the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import contextlib
+import importlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "vocoder_audio_seconds_per_second"
+UNIT = "audio-s/s"
+SR = 22050
+HOP = 256
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step")
+    ap.add_argument("--frames", type=int, default=861, help="mel frames per utterance (861 = 10 s)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--act-sweep", action="store_true", help="also print the fused-activation HBM sweep (config 3)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_forward_rate(h, sd, frames, runs, threads):
+    """audio-s per wall-s of the oracle port (reference torch algorithm) on the host cores."""
+    import torch
+    from oracle import bigvgan_oracle as O
+    synth = importlib.import_module("voice-tts_b200.synth")
+    torch.set_num_threads(threads)
+    mel = synth.make_mel(1, h["num_mels"], frames)
+    with torch.no_grad():
+        O.generator_forward(sd, h, mel)  # warm-up
+        ts = []
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            O.generator_forward(sd, h, mel)
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return frames * HOP / SR / med, med
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    import torch
+    cfg = importlib.import_module("voice-tts_b200.config")
+    synth = importlib.import_module("voice-tts_b200.synth")
+    from oracle import bigvgan_oracle as O
+    h = cfg.default_hparams()
+    sd = synth.make_state_dict(h, seed=1234)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    # size the per-step sample so that the whole run stays within ~2.5 minutes
+    probe_frames = 43
+    rate, t_probe = cpu_forward_rate(h, sd, probe_frames, 1, threads)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    frames = int(max(22, min(args.frames, probe_frames * budget / t_probe)))
+    mel = synth.make_mel(1, h["num_mels"], frames)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.generator_forward(sd, h, mel)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.generator_forward(sd, h, mel)
+        dt = time.perf_counter() - t0
+    audio_s = frames * HOP / SR
+    value = audio_s * args.steps / dt
+    sample = "1 utterance x %d mel frames (%.2f s audio) per step, fp32, torch %s CPU, %s" % (
+        frames, audio_s, torch.__version__, cpu_model_name())
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "bigvgan_v2_22khz_80band_256x, batch %d x %d frames per GPU (CPU arm: bounded sample)"
+                               % (args.batch, args.frames), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def act_sweep(dev, pk):
+    """BASELINE config 3: fused Activation1d HBM sweep on [B,C,T] (operator layout)."""
+    import torch
+    ops = importlib.import_module("voice-tts_b200.ops")
+    from oracle import bigvgan_oracle as O
+    taps = O.kaiser_taps().tolist()
+    rows = []
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for dt in (torch.bfloat16, torch.float32):
+        for C in (24, 48, 192, 768, 1536):
+            for T in (8192, 131072, 2097152):
+                es = 2 if dt == torch.bfloat16 else 4
+                B = max(1, min(64, (256 << 20) // (C * T * es)))
+                if B * C * T * es > (3 << 30):
+                    continue
+                x = torch.randn(B, C, T, device=dev).to(dt)
+                a = torch.randn(C, device=dev) * 0.5
+                b = torch.randn(C, device=dev) * 0.5
+                fast = dt == torch.bfloat16
+                for _ in range(2):
+                    ops.act1d(x, a, b, taps, taps, fast)
+                ts = []
+                for _ in range(5):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    ops.act1d(x, a, b, taps, taps, fast)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ts.sort()
+                gbs = 2.0 * B * C * T * es / (ts[len(ts) // 2] * 1e-3) / 1e9
+                rows.append({"dtype": str(dt)[6:], "B": B, "C": C, "T": T, "ms": ts[len(ts) // 2], "GBps": round(gbs, 1),
+                             "frac_hbm": round(gbs / pk["hbm_gbs"], 3)})
+                del x
+    return rows
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    pkg = importlib.import_module("voice-tts_b200")
+    cfg = importlib.import_module("voice-tts_b200.config")
+    synth = importlib.import_module("voice-tts_b200.synth")
+    _lib = importlib.import_module("voice-tts_b200._lib")
+    shard = importlib.import_module("voice-tts_b200.shard")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    h = cfg.default_hparams()
+    sd = synth.make_state_dict(h, seed=1234)
+    model = pkg.BigVGAN(h, precision=args.precision)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.remove_weight_norm()
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    model.set_option("profile", 1)
+
+    B, T0 = args.batch, args.frames
+    audio_s_step = B * T0 * HOP / SR
+    # utterances are sharded by rank (weak scaling: B per GPU): rank r vocodes [r*B, (r+1)*B) of the global batch
+    lo, hi = shard.shard_range(B * world, rank, world)
+    mel_host = synth.make_mel(hi - lo, h["num_mels"], T0, first_utterance=lo).pin_memory()
+    mel = mel_host.to(dev, non_blocking=True)
+    wav_host = torch.empty(B, 1, T0 * cfg.total_upsample(h), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        return shard.max_over_ranks(x, dev)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            wav = model(mel)
+        torch.cuda.synchronize()
+        model.read_profile()  # drop warm-up records
+
+        # ---- device-resident throughput: K steps, CUDA events, max over ranks ----
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            wav = model(mel)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - n0
+        clocks = sampler.stop() if rank == 0 else None
+        prof = model.read_profile()
+        ms = max_over_ranks(ms)
+
+        # ---- end to end through the host-buffer C ABI call ----
+        model.set_option("profile", 0)
+        for _ in range(2):
+            model.forward_host(mel_host, out=wav_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model.forward_host(mel_host, out=wav_host)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+
+    value = world * audio_s_step * args.steps / (ms * 1e-3)
+    e2e_value = world * audio_s_step * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations of this run) ----
+    c_ms, c_flops, c_n = prof["conv_tcgen05"]
+    s_ms, s_flops, s_n = prof["conv_simt"]
+    a_ms, a_bytes, a_n = prof["activation"]
+    o_ms, _, o_n = prof["other"]
+    tot = c_ms + s_ms + a_ms + o_ms
+    conv_ms, conv_flops, conv_n, conv_name = (c_ms, c_flops, c_n, "conv_umma_kernel (tcgen05 implicit-GEMM Conv1d/ConvTranspose1d)") \
+        if c_n else (s_ms, s_flops, s_n, "conv_simt_kernel (fp32)")
+    tensor_peak = pk["bf16_tflops_sustained"]
+    ach_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    ach_gb = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
+    roofline = {"kernel": conv_name, "bound": "tensor", "achieved": round(ach_tf, 2), "peak": tensor_peak,
+                "unit": "TFLOP/s", "frac": round(ach_tf / tensor_peak, 4), "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
+                "share_of_step": round(conv_ms / tot, 3) if tot else None, "launches": conv_n,
+                "avg_launch_ms": round(conv_ms / max(conv_n, 1), 4)}
+    roofline_act = {"kernel": "act1d_cl_kernel (fused up2-snakebeta-down2, channels-last)", "bound": "hbm",
+                    "achieved": round(ach_gb, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": None,
+                    "share_of_step": round(a_ms / tot, 3) if tot else None, "launches": a_n}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "bigvgan_v2_22khz_80band_256x generator, %d utterances x %d mel frames (%.1f s) per GPU per step"
+                               % (B, T0, T0 * HOP / SR),
+                   "global_batch": B * world, "parallelism": "batch-sharded x%d, no collective" % world,
+                   "weights": "random-init (seed 1234), alpha/beta ~ N(0,0.5)",
+                   "l2": "no explicit flush: each step streams a %.1f GB workspace + 0.22 GB weights (>> 126 MB L2)"
+                         % (model_workspace_gb(model, B, T0))},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4,
+                "d2h_bytes_per_step": wav_host.numel() * 4, "api": "BigVGAN.forward_host -> bvg_vocoder_fwd_host"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_activation": roofline_act,
+        "time_split_ms_per_step": {"conv_tcgen05": c_ms / args.steps, "conv_simt": s_ms / args.steps,
+                                   "activation": a_ms / args.steps, "other": o_ms / args.steps},
+        "x_realtime_per_gpu": value / world,
+    }
+
+    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+        threads = os.cpu_count() or 1
+        # bounded sample: one 2 s utterance (BASELINE configs[0]) - ~10-30 s of CPU work
+        rate, med = cpu_forward_rate(h, sd, 172, 3, threads)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": "oracle port of the reference torch path, fp32, 1 utterance x 172 frames (2.0 s), "
+                                         "median of 3 after 1 warm-up, %.2f s per forward, %s" % (med, cpu_model_name())}
+    if rank == 0 and args.act_sweep:
+        out["activation_sweep"] = act_sweep(dev, pk)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def model_workspace_gb(model, B, T0):
+    _lib = importlib.import_module("voice-tts_b200._lib")
+    ops = importlib.import_module("voice-tts_b200.ops")
+    if model._hid is None:
+        return 0.0
+    return _lib.load().bvg_workspace_bytes(ops._HANDLES[model._hid][0], B, T0) / 1e9
+
+
+if __name__ == "__main__":
+    main()

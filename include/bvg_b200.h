@@ -142,8 +142,14 @@ int bvg_vocoder_fwd(bvg_vocoder* v, const float* mel, float* wav, int B, int T0,
  * wav_dtype: 0 = fp32 wav in [-1,1]; 1 = int16 `clamp(32767*wav, -32767, 32767)` (infer_v2.py:740). */
 int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, int wav_dtype,
                          int B, int T0, bvg_stream_t stream);
-/* options: "graph" (0/1, CUDA-graph the layer sequence), "conv_impl" (0 auto, 1 simt, 2 umma) */
+/* options: "graph" (0/1, CUDA-graph the layer sequence), "conv_impl" (0 auto, 1 simt, 2 tcgen05),
+ * "fast_sin" (0/1), "workspace_mb" (micro-batching cap), "profile" (0/1) */
 int bvg_set_option(bvg_vocoder* v, const char* key, int value);
+/* per-kernel CUDA-event timing (set option "profile"=1 first; disables graph replay while on):
+ * category 0 = tcgen05 conv, 1 = SIMT conv, 2 = fused activation, 3 = other.  Returns the summed
+ * duration [ms], the summed algorithmic work (flops for convs, bytes for activations) and the
+ * number of launches since the last read; reading category 3 clears the records. */
+int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double* work, int* launches);
 /* introspection for benchmarks: kernels launched by the last forward */
 int bvg_last_forward_launches(const bvg_vocoder* v);
 

@@ -1,0 +1,133 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol
+include/bvg_b200.h declares (no compute without a GPU), drop-in classes keep the
+reference's state-dict layout, sharding logic incl. a world_size-2 gloo run, and
+the reference arm of bench.py."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import importlib
+    importlib.import_module("__graft_entry__").build()
+    _lib = importlib.import_module("voice-tts_b200._lib")
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "bvg_b200.h")).read()
+    declared = set(re.findall(r"\b(bvg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SYMBOLS.keys())
+    assert lib.bvg_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import importlib
+    _lib = importlib.import_module("voice-tts_b200._lib")
+    lib = _lib.load()
+    cfg = _lib.BvgConfig()
+    cfg.num_mels, cfg.upsample_initial_channel, cfg.num_upsamples, cfg.num_kernels, cfg.num_dilations = 8, 32, 1, 1, 1
+    cfg.upsample_rates[0], cfg.upsample_kernel_sizes[0], cfg.resblock_kernel_sizes[0] = 2, 4, 3
+    cfg.resblock_dilations[0][0] = 1
+    cfg.mode = 1
+    h = ctypes.c_void_p()
+    rc = lib.bvg_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc in (-5, -4) and not h.value          # BVG_ENODEV / BVG_ECUDA: no fallback
+    assert lib.bvg_last_error()
+    taps = _lib.taps_array([0.0] * 12)
+    buf = (ctypes.c_float * 16)()
+    rc = lib.bvg_act1d_fwd(ctypes.addressof(buf), ctypes.addressof(buf) + 32, ctypes.addressof(buf), ctypes.addressof(buf),
+                           taps, taps, 1, 1, 4, 0, 0, None)
+    assert rc < 0
+    # argument validation happens before any device work
+    assert lib.bvg_act1d_fwd(None, None, None, None, taps, taps, 1, 1, 4, 7, 0, None) == -2   # BVG_EDTYPE
+    assert lib.bvg_act1d_fwd(None, None, None, None, taps, taps, 1, 1, 0, 0, 0, None) == 0    # T == 0: no-op
+    ops = importlib.import_module("voice-tts_b200.ops")
+    with pytest.raises(RuntimeError):
+        ops.act1d(torch.zeros(1, 2, 8), torch.zeros(2), torch.zeros(2), [0.0] * 12, [0.0] * 12, False)
+
+
+def test_dropin_state_dict_layout(pkg, synth, cfg):
+    h = cfg.default_hparams()
+    names = [k for k, _, _ in synth.state_dict_spec(h)]
+    tiny = cfg.tiny_hparams()
+    m = pkg.BigVGAN(tiny)
+    wn_keys = set(m.state_dict().keys())
+    assert "conv_pre.weight_g" in wn_keys and "resblocks.0.convs1.0.weight_v" in wn_keys
+    m.remove_weight_norm()
+    m.remove_weight_norm()   # idempotent like the reference (bigvgan.py:388-400)
+    sd = synth.make_state_dict(tiny, 1)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd)
+    a = m.resblocks[0].activations[0]
+    assert hasattr(a, "act") and hasattr(a.upsample, "filter") and hasattr(a.downsample.lowpass, "filter")
+    assert len(names) == 667
+    f = m.folded_state_dict()
+    assert all(torch.equal(f[k], sd[k]) for k in sd)
+    with pytest.raises(ValueError):
+        pkg.BigVGAN(cfg.tiny_hparams(resblock="2"))
+
+
+def test_shard_ranges_and_chunks():
+    import importlib
+    shard = importlib.import_module("voice-tts_b200.shard")
+    for n in (0, 1, 7, 16, 256):
+        for world in (1, 2, 4, 8):
+            covered = []
+            for r in range(world):
+                lo, hi = shard.shard_range(n, r, world)
+                covered += list(range(lo, hi))
+                assert hi - lo in (n // world, n // world + 1)
+            assert covered == list(range(n))
+    chunks = shard.split_chunks(2584, 600)
+    assert chunks[0][:2] == (0, 634) and chunks[-1][1] == 2584
+    assert sum(k1 - k0 for _, _, k0, k1 in chunks) == 2584
+
+
+def test_gloo_world2_sharding_and_timing_reduce(tmp_path):
+    """world_size-2 gloo run of the sharding/timing logic bench.py uses under torchrun."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, importlib, torch, torch.distributed as dist\n"
+        "sys.path.insert(0, %r)\n"
+        "shard = importlib.import_module('voice-tts_b200.shard')\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "lo, hi = shard.shard_range(16 * w, r, w)\n"
+        "mel = torch.arange(16 * w).float().view(-1, 1, 1).repeat(1, 2, 3)\n"
+        "lo2, hi2, out = shard.vocode_sharded(lambda m: m.sum(dim=(1, 2), keepdim=True), mel, r, w)\n"
+        "assert (lo, hi) == (lo2, hi2) == (16 * r, 16 * r + 16)\n"
+        "got = [torch.zeros_like(out) for _ in range(w)]\n"
+        "dist.all_gather(got, out)\n"
+        "assert torch.equal(torch.cat(got).view(-1), torch.arange(16 * w).float() * 6)\n"
+        "m = shard.max_over_ranks(10.0 + r)\n"
+        "assert m == 10.0 + (w - 1)\n"
+        "dist.barrier(); print('ok', r)\n" % ROOT)
+    import socket
+    with socket.socket() as sk:          # a free port: fixed ports collide when suites run back to back
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    assert "ok 0" in out.stdout and "ok 1" in out.stdout
+
+
+def test_bench_reference_arm_prints_contract_json():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--frames", "22"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "audio-s/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

@@ -219,6 +219,19 @@ class BigVGAN(nn.Module):
         _lib.check(rc, "bvg_vocoder_fwd_host")
         return out
 
+    def read_profile(self):
+        """{category: (ms, algorithmic work, launches)} since the last read (option profile=1)."""
+        import ctypes
+        out = {}
+        if self._hid is None:
+            return out
+        for cat, name in enumerate(("conv_tcgen05", "conv_simt", "activation", "other")):
+            ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+            _lib.check(_lib.load().bvg_profile_read(ops._HANDLES[self._hid][0], cat, ctypes.byref(ms),
+                                                    ctypes.byref(work), ctypes.byref(n)), "bvg_profile_read")
+            out[name] = (ms.value, work.value, n.value)
+        return out
+
     def last_forward_launches(self):
         return 0 if self._hid is None else int(_lib.load().bvg_last_forward_launches(ops._HANDLES[self._hid][0]))
 

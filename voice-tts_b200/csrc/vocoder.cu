@@ -70,6 +70,11 @@ struct bvg_vocoder {
   float* dev_mel = nullptr; size_t dev_mel_bytes = 0;
   void* dev_wav = nullptr;  size_t dev_wav_bytes = 0;
   int last_launches = 0;
+  // per-kernel CUDA-event profiling (option "profile"): category -> accumulated work; events resolved on read
+  struct ProfRec { int cat; double work; cudaEvent_t e0, e1; };
+  int opt_profile = 0;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int>> graphs;  // exec + kernels inside
 };
 
@@ -158,6 +163,24 @@ static int max_microbatch(const bvg_vocoder* v, int B, int T0) {
   return b;
 }
 
+enum { CAT_CONV_UMMA = 0, CAT_CONV_SIMT = 1, CAT_ACT = 2, CAT_OTHER = 3, CAT_N = 4 };
+
+static cudaEvent_t prof_event(bvg_vocoder* v) {
+  cudaEvent_t e = nullptr;
+  if (!v->ev_pool.empty()) { e = v->ev_pool.back(); v->ev_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  bvg_vocoder* v; cudaStream_t st; int cat; double work; cudaEvent_t e0 = nullptr;
+  ProfScope(bvg_vocoder* v_, cudaStream_t st_, int cat_, double work_) : v(v_), st(st_), cat(cat_), work(work_) {
+    if (v->opt_profile) { e0 = prof_event(v); cudaEventRecord(e0, st); }
+  }
+  ~ProfScope() {
+    if (e0) { cudaEvent_t e1 = prof_event(v); cudaEventRecord(e1, st); v->prof.push_back({cat, work, e0, e1}); }
+  }
+};
+
 static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, void* out, int out_dt,
                     const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st) {
   ConvArgs a;
@@ -170,12 +193,16 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
     if (v->opt_conv_impl == 2) BVG_FAIL(BVG_EINVAL, "conv layer not supported by the tcgen05 kernel");
     umma = false;
   }
+  // algorithmic flops: 2*Cout*Cin*k*T_out*B (Conv1d) / 2*Cin*Cout*k*T_in*B (ConvTranspose1d), unpadded channels
+  ProfScope ps(v, st, umma ? CAT_CONV_UMMA : CAT_CONV_SIMT, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   return umma ? conv_umma_launch(a, v->opt_umma_variant, st) : conv_simt_launch(a, st);
 }
 
 static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, void* out, int out_dt, int B,
                    int64_t T, cudaStream_t st) {
   const bool fast = v->opt_fast_sin >= 0 ? v->opt_fast_sin != 0 : v->cfg.mode == BVG_MODE_BF16;
+  // algorithmic bytes: one read + one write of the unpadded tensor
+  ProfScope ps(v, st, CAT_ACT, (double)B * T * a.C * (dtype_size(in_dt) + dtype_size(out_dt)));
   return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, a.Cp, in_dt, out_dt, fast, st);
 }
 
@@ -223,9 +250,13 @@ static int forward_chunk(bvg_vocoder* v, const float* mel, void* wav, int wav_i1
                          cudaStream_t st) {
   Buffers bf;
   plan_buffers(v, B, T0, &bf);
-  int rc = bct_to_btc(bf.mel, v->act_dt, mel, B, v->cfg.num_mels, v->mel_p, T0, st);
+  int rc;
+  {
+    ProfScope ps(v, st, CAT_OTHER, 0.0);
+    rc = bct_to_btc(bf.mel, v->act_dt, mel, B, v->cfg.num_mels, v->mel_p, T0, st);
+  }
   if (rc) return rc;
-  if (v->opt_graph) {
+  if (v->opt_graph && !v->opt_profile) {
     auto key = std::make_pair(B, T0);
     auto it = v->graphs.find(key);
     if (it == v->graphs.end()) {
@@ -253,6 +284,7 @@ static int forward_chunk(bvg_vocoder* v, const float* mel, void* wav, int wav_i1
     if (rc) return rc;
   }
   const int64_t Tw = (int64_t)T0 * v->total_up;
+  ProfScope ps(v, st, CAT_OTHER, 0.0);
   return conv_post_launch(wav, wav_i16, bf.a1, v->act_dt, v->post_w, v->post_bias, B, v->Cp[v->nst], Tw,
                           v->cfg.use_tanh_at_final, st);
 }
@@ -591,6 +623,8 @@ extern "C" void bvg_destroy(bvg_vocoder* v) {
   for (auto& a : v->acts) free_act(a);
   free_act(v->act_post);
   if (v->post_w) cudaFree(v->post_w);
+  for (auto& r : v->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto& e : v->ev_pool) cudaEventDestroy(e);
   for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
   if (v->arena) cudaFree(v->arena);
   if (v->pin_mel) cudaFreeHost(v->pin_mel);
@@ -607,7 +641,29 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
   else if (!strcmp(key, "umma_variant")) v->opt_umma_variant = value;
   else if (!strcmp(key, "fast_sin")) v->opt_fast_sin = value;
   else if (!strcmp(key, "workspace_mb")) v->opt_ws_cap_mb = value;
+  else if (!strcmp(key, "profile")) v->opt_profile = value;
   else BVG_FAIL(BVG_EINVAL, "bvg_set_option: unknown option '%s'", key);
+  return BVG_OK;
+}
+
+// Sums the CUDA-event durations recorded since the last read for one category
+// (0 tcgen05 conv, 1 SIMT conv, 2 fused activation, 3 other) and clears them when
+// category 3 (the last one) is read.  Synchronises the device.
+extern "C" int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double* work, int* launches) {
+  if (!v || category < 0 || category >= CAT_N || !ms || !work || !launches) BVG_FAIL(BVG_EINVAL, "bvg_profile_read: bad argument");
+  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  BVG_CUDA(cudaDeviceSynchronize());
+  *ms = 0; *work = 0; *launches = 0;
+  for (auto& r : v->prof) {
+    if (r.cat != category) continue;
+    float t = 0.f;
+    BVG_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    *ms += t; *work += r.work; *launches += 1;
+  }
+  if (category == CAT_N - 1) {
+    for (auto& r : v->prof) { v->ev_pool.push_back(r.e0); v->ev_pool.push_back(r.e1); }
+    v->prof.clear();
+  }
   return BVG_OK;
 }
 
