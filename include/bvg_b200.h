@@ -150,6 +150,8 @@ int bvg_set_option(bvg_vocoder* v, const char* key, int value);
  * duration [ms], the summed algorithmic work (flops for convs, bytes for activations) and the
  * number of launches since the last read; reading category 3 clears the records. */
 int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double* work, int* launches);
+/* writes one CSV line per recorded launch (category, shape, ms, work, rate) to `path`; does not clear */
+int bvg_profile_dump(bvg_vocoder* v, const char* path);
 /* introspection for benchmarks: kernels launched by the last forward */
 int bvg_last_forward_launches(const bvg_vocoder* v);
 

@@ -21,6 +21,7 @@ def bf(x):
 CONV_CASES = [  # B, Cin, Cout, T, k, dil
     (1, 16, 16, 50, 3, 1), (2, 24, 24, 300, 11, 5), (1, 80, 200, 64, 7, 1), (1, 12, 12, 77, 7, 3),
     (1, 96, 96, 1000, 7, 3), (2, 48, 48, 513, 3, 5), (1, 192, 192, 256, 11, 1), (1, 1, 5, 9, 3, 1),
+    (2, 48, 80, 700, 3, 1), (1, 16, 144, 300, 7, 1), (3, 32, 48, 1031, 11, 3),   # partially filled 128-channel tiles
 ]
 
 

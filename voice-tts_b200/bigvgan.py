@@ -232,6 +232,9 @@ class BigVGAN(nn.Module):
             out[name] = (ms.value, work.value, n.value)
         return out
 
+    def dump_profile(self, path):
+        _lib.check(_lib.load().bvg_profile_dump(ops._HANDLES[self._hid][0], str(path).encode()), "bvg_profile_dump")
+
     def last_forward_launches(self):
         return 0 if self._hid is None else int(_lib.load().bvg_last_forward_launches(ops._HANDLES[self._hid][0]))
 

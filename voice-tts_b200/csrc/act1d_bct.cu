@@ -71,7 +71,60 @@ act1d_bct_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __
   const int64_t tlast = Tlen - 1;
 
   if (t0 < t1) {
-    float X[6], V[12], vend = 0.f;
+    float X[6], V[12];
+    if (t0 >= 5 && t0 + L + 4 <= tlast && t1 - t0 == L) {
+      // ---- interior segment (L = 6n-5 -> L+5 steps = n bodies of 6): no clamps/edge rules/predicates ----
+      const T* ip = s_in + (t0 - 5 - lo);
+      T* op = s_out + (t0 - tile_t0);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) X[i] = to_f32<T>(ip[i]);
+      ip += 5;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {   // first body: 5 warm-up steps + 1 full step
+        X[(s + 5) % 6] = to_f32<T>(ip[s]);
+        float uo = 0.f, ue = 0.f;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float xv = X[(s + 5 - q) % 6];
+          uo = fmaf(taps.up[2 * q], xv, uo);
+          ue = fmaf(taps.up[2 * q + 1], xv, ue);
+        }
+        V[(2 * s + 10) % 12] = snake_eval<FAST>(uo, a, ib);
+        V[(2 * s + 11) % 12] = snake_eval<FAST>(ue, a, ib);
+        if (s == 5) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) acc = fmaf(taps.down[k], V[(2 * s + k) % 12], acc);
+          op[0] = from_f32<T>(acc);
+        }
+      }
+      ip += 6;
+      op += 1;
+      const int nbody = (L + 5) / 6 - 1;
+      for (int it = 0; it < nbody; ++it) {
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+          X[(s + 5) % 6] = to_f32<T>(ip[s]);
+          float uo = 0.f, ue = 0.f;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const float xv = X[(s + 5 - q) % 6];
+            uo = fmaf(taps.up[2 * q], xv, uo);
+            ue = fmaf(taps.up[2 * q + 1], xv, ue);
+          }
+          V[(2 * s + 10) % 12] = snake_eval<FAST>(uo, a, ib);
+          V[(2 * s + 11) % 12] = snake_eval<FAST>(ue, a, ib);
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) acc = fmaf(taps.down[k], V[(2 * s + k) % 12], acc);
+          op[s] = from_f32<T>(acc);
+        }
+        ip += 6;
+        op += 6;
+      }
+    } else {
+    // ---- generic segment: touches a row end or is short ----
+    float vend = 0.f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       int64_t ti = t0 - 5 + i;
@@ -120,6 +173,7 @@ act1d_bct_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __
         if (t >= t0 && t < t1) s_out[t - tile_t0] = from_f32<T>(acc);
       }
     }
+    }
   }
 
   const int n_out = (int)(tile_end - tile_t0);
@@ -149,8 +203,8 @@ static int launch_bct(void* dst, const void* src, const float* alpha_log, const 
   const int tiles_per_row = (int)ceil_div(Tlen, max_tile);
   const int64_t per_tile = ceil_div(Tlen, tiles_per_row);
   int L = (int)ceil_div(per_tile, kBctThreads);
-  if (L % 2 == 0) L += 1;           // odd stride => conflict-free shared-memory walk
-  if (L < 3) L = 3;                 // only the first segment of a row may see v[m<0] (needs 2*L-5 >= 0)
+  L = (int)ceil_div(L + 5, 6) * 6 - 5;  // 6n-5: whole 6-step bodies; odd => conflict-free shared-memory walk
+  if (L < 7) L = 7;                 // only the first segment of a row may see v[m<0] (needs 2*L-5 >= 0)
   if (L > kBctMaxSeg) L = kBctMaxSeg;
   const int tile_len = kBctThreads * L;   // multiple of 128 elements
   const int64_t blocks = rows * tiles_per_row;

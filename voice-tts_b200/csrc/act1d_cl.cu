@@ -56,6 +56,28 @@ struct VecIO<__nv_bfloat16, 2> {
   }
 };
 
+// One time step of the sliding window for VEC channels.  S is the step index
+// modulo 6 (compile time after unrolling): slot (S+5)%6 of X receives x[t+5],
+// slots (2S+10)%12,(2S+11)%12 of V receive v[2t+5], v[2t+6].
+#define BVG_ACT_UP(S, X, taps, a, ib, vo, ve)                              \
+  _Pragma("unroll") for (int j = 0; j < VEC; ++j) {                        \
+    float uo = 0.f, ue = 0.f;                                              \
+    _Pragma("unroll") for (int q = 0; q < 6; ++q) {                        \
+      const float xv = X[((S) + 5 - q) % 6][j];                            \
+      uo = fmaf(taps.up[2 * q], xv, uo);                                   \
+      ue = fmaf(taps.up[2 * q + 1], xv, ue);                               \
+    }                                                                      \
+    vo[j] = snake_eval<FAST>(uo, a[j], ib[j]);                             \
+    ve[j] = snake_eval<FAST>(ue, a[j], ib[j]);                             \
+  }
+#define BVG_ACT_DOWN(S, V, taps, y)                                        \
+  _Pragma("unroll") for (int j = 0; j < VEC; ++j) {                        \
+    float acc = 0.f;                                                       \
+    _Pragma("unroll") for (int k = 0; k < 12; ++k)                         \
+      acc = fmaf(taps.down[k], V[(2 * (S) + k) % 12][j], acc);             \
+    y[j] = acc;                                                            \
+  }
+
 template <typename Tin, typename Tout, int VEC, bool FAST>
 __global__ void __launch_bounds__(128)
 act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
@@ -85,19 +107,64 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
 
   float X[6][VEC];    // slot p holds x at time == p (mod 6) relative to the first step
   float V[12][VEC];   // slot p holds v at index == p (mod 12) relative to the first step
+
+  // steps run over t = t0-5 .. t1-1; step t loads x[t+5] and produces v[2t+5], v[2t+6], y[t].
+  if (t0 >= 5 && t0 + L + 4 <= tlast) {
+    // ---- interior segment (L = 6n-5): no clamps, no edge fixes, no predicates ----
+    const Tin* lp = sp + (t0 - 5) * C;
+    Tout* op = dp + t0 * C;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { VecIO<Tin, VEC>::load(lp, X[i]); lp += C; }
+    float XN[6][VEC];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { VecIO<Tin, VEC>::load(lp, XN[i]); lp += C; }
+    // first body: 5 warm-up steps (no output) + 1 full step
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) X[(s + 5) % 6][j] = XN[s][j];
+      float vo[VEC], ve[VEC];
+      BVG_ACT_UP(s, X, taps, a, ib, vo, ve)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { V[(2 * s + 10) % 12][j] = vo[j]; V[(2 * s + 11) % 12][j] = ve[j]; }
+      if (s == 5) {
+        float y[VEC];
+        BVG_ACT_DOWN(s, V, taps, y)
+        VecIO<Tout, VEC>::store(op, y);
+        op += C;
+      }
+    }
+    const int nbody = (L + 5) / 6 - 1;
+    for (int it = 0; it < nbody; ++it) {
+      // loads of this body: issued up front, consumed step by step
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { VecIO<Tin, VEC>::load(lp, XN[i]); lp += C; }
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) X[(s + 5) % 6][j] = XN[s][j];
+        float vo[VEC], ve[VEC], y[VEC];
+        BVG_ACT_UP(s, X, taps, a, ib, vo, ve)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { V[(2 * s + 10) % 12][j] = vo[j]; V[(2 * s + 11) % 12][j] = ve[j]; }
+        BVG_ACT_DOWN(s, V, taps, y)
+        VecIO<Tout, VEC>::store(op, y);
+        op += C;
+      }
+    }
+    return;
+  }
+
+  // ---- generic segment: touches a sequence end (replicate clamps, v edge rules) or is short ----
   float vend[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) vend[j] = 0.f;
-
-  // steps run over t = t0-5 .. t1-1; step t loads x[t+5] and produces v[2t+5], v[2t+6], y[t].
-  // preload x[t0-5 .. t0-1] into slots 0..4
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
     int64_t ti = t0 - 5 + i;
     ti = ti < 0 ? 0 : (ti > tlast ? tlast : ti);
     VecIO<Tin, VEC>::load(sp + ti * C, X[i]);
   }
-
   const int nsteps = (int)(t1 - t0) + 5;
   for (int base = 0; base < nsteps; base += 6) {
 #pragma unroll
@@ -106,20 +173,8 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
       int64_t tl = t + 5;
       tl = tl > tlast ? tlast : tl;  // t+5 >= 0 always
       VecIO<Tin, VEC>::load(sp + tl * C, X[(s + 5) % 6]);
-
       float vo[VEC], ve[VEC];
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        float uo = 0.f, ue = 0.f;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const float xv = X[(s + 5 - q) % 6][j];
-          uo = fmaf(taps.up[2 * q], xv, uo);
-          ue = fmaf(taps.up[2 * q + 1], xv, ue);
-        }
-        vo[j] = snake_eval<FAST>(uo, a[j], ib[j]);  // v[2t+5]
-        ve[j] = snake_eval<FAST>(ue, a[j], ib[j]);  // v[2t+6]
-      }
+      BVG_ACT_UP(s, X, taps, a, ib, vo, ve)
       // right edge: v[m >= 2T] := v[2T-1]; v[2T-1] is the odd sample of step T-3
       if (t >= T - 3) {
 #pragma unroll
@@ -130,30 +185,17 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
         }
       }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        V[(2 * s + 10) % 12][j] = vo[j];
-        V[(2 * s + 11) % 12][j] = ve[j];
-      }
+      for (int j = 0; j < VEC; ++j) { V[(2 * s + 10) % 12][j] = vo[j]; V[(2 * s + 11) % 12][j] = ve[j]; }
       // left edge: v[m < 0] := v[0]; with t0 == 0, v[0] is the even sample of the 3rd step
       if (s == 2 && base == 0 && t0 == 0) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           const float v0 = V[3][j];
-          V[10][j] = v0;
-          V[11][j] = v0;
-          V[0][j] = v0;
-          V[1][j] = v0;
-          V[2][j] = v0;
+          V[10][j] = v0; V[11][j] = v0; V[0][j] = v0; V[1][j] = v0; V[2][j] = v0;
         }
       }
       float y[VEC];
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) acc = fmaf(taps.down[k], V[(2 * s + k) % 12][j], acc);
-        y[j] = acc;
-      }
+      BVG_ACT_DOWN(s, V, taps, y)
       if (t >= t0 && t < t1) VecIO<Tout, VEC>::store(dp + t * C, y);
     }
   }

@@ -34,7 +34,9 @@ constexpr int UM_X_STAGES = 2;
 constexpr int UM_A_STAGE_BYTES = UM_M * 128;      // 128 rows x (<=128 B)
 constexpr int UM_MAX_X_ROWS = 320;                // NT + (k-1)*dil rounded to 2 boxes of <=160 rows
 constexpr int UM_X_STAGE_BYTES = UM_MAX_X_ROWS * 128;
-constexpr int UM_SMEM_BYTES = 1024 /*align slack*/ + UM_A_STAGES * UM_A_STAGE_BYTES + UM_X_STAGES * UM_X_STAGE_BYTES + 256;
+constexpr int UM_EPI_BUF_BYTES = 32 * UM_M * 4;     // one staged [32 time rows][<=128 channels] fp32 block
+constexpr int UM_SMEM_BYTES = 1024 /*align slack*/ + UM_A_STAGES * UM_A_STAGE_BYTES + UM_X_STAGES * UM_X_STAGE_BYTES +
+                              2 * UM_EPI_BUF_BYTES + 256;
 
 struct UmmaParams {
   const float* bias;
@@ -78,7 +80,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* a_st = smem;
   unsigned char* x_st = smem + UM_A_STAGES * UM_A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(x_st + UM_X_STAGES * UM_X_STAGE_BYTES);
+  float* epi_st = reinterpret_cast<float*>(x_st + UM_X_STAGES * UM_X_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_st + UM_X_STAGES * UM_X_STAGE_BYTES + 2 * UM_EPI_BUF_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + UM_A_STAGES;
   uint64_t* x_full = a_empty + UM_A_STAGES;
@@ -199,49 +202,96 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else {
     // -------------------------------------------------- epilogue warps 2..5
+    // TMEM (lane = out-channel, column = time) -> registers -> shared [time][channel] block ->
+    // 16-byte vector global accesses that are contiguous along channels (and across rows when
+    // the layer has <= 128 channels).  Residual / accumulate operands are loaded before any
+    // store of the same block, so the loads are not serialised behind possibly aliasing stores.
     const int g = warp % 4;               // TMEM lane group this warp may access
+    const int etid = (warp - 2) * 32 + lane;   // 0..127 among the epilogue threads
     uint32_t acc = 0, accph = 0;
+    uint32_t blk = 0;                     // running 32-column block counter -> staging buffer parity
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int cot = (int)(tile % p.n_cotiles);
       const int64_t r = tile / p.n_cotiles;
       const int tt = (int)(r % p.n_ttiles);
       const int b = (int)(r / p.n_ttiles);
       const int t0 = tt * p.NT;
-      const int co = cot * UM_M + g * 32 + lane;
-      const bool warp_active = (cot * UM_M + g * 32) < p.Cout_n;
-      const bool co_ok = co < p.Cout_n;
-      const float bv = (p.bias && co_ok) ? __ldg(p.bias + co) : 0.f;
+      const int co0 = cot * UM_M;
+      const int cv = (p.Cout_n - co0) < UM_M ? (p.Cout_n - co0) : UM_M;   // valid channels of this tile (multiple of 16)
+      const int vpr = cv >> 2;                                             // float4 vectors per time row
+      const uint32_t vpr_magic = (65536u + (uint32_t)vpr - 1) / (uint32_t)vpr;  // e / vpr for e < 4096
+      const bool warp_has_rows = g * 32 < cv;
+      const int nvec = 32 * vpr;                                           // vectors per 32-column block
+      const int64_t tilebase = ((int64_t)b * p.T + t0) * p.out_ld + co0;
 
       mbar_wait(&t_full[acc], accph);
       tc_fence_after();
-      if (warp_active) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * (uint32_t)p.NT;
-        const int64_t rowbase = ((int64_t)b * p.T + t0) * p.out_ld + co;
-        for (int nb = 0; nb < p.NT; nb += 32) {
-          if (t0 + nb >= p.T) break;
+      const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * (uint32_t)p.NT;
+      int nb_end = p.T - t0;                                               // valid time rows in this tile
+      if (nb_end > p.NT) nb_end = p.NT;
+      for (int nb = 0; nb < nb_end; nb += 32, ++blk) {
+        float* sbuf = epi_st + (blk & 1) * (UM_EPI_BUF_BYTES / 4);
+        if (warp_has_rows) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + nb, v);
           tmem_ld_wait();
+          const int col = g * 32 + lane;
+          if (col < cv) {   // cv is a multiple of 16: the last warp with rows may be half valid
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int t = t0 + nb + i;
-            if (t < p.T && co_ok) {
-              const int64_t off = rowbase + (int64_t)(nb + i) * p.out_ld;
-              float y = __uint_as_float(v[i]) + bv;
-              if (p.res) y += __ldg(p.res + off);
-              y *= p.scale;
-              if (p.accum) y += __ldg(p.accum + off);
-              if (p.out_bf16)
-                reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(y);
-              else
-                reinterpret_cast<float*>(p.out)[off] = y;
+            for (int i = 0; i < 32; ++i) sbuf[i * cv + col] = __uint_as_float(v[i]);
+          }
+        }
+        if (nb + 32 >= nb_end) {           // all TMEM reads of this tile are done: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[acc]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int rows_here = (nb_end - nb) < 32 ? (nb_end - nb) : 32;
+        const int nvalid = rows_here * vpr;
+        const int64_t blkbase = tilebase + (int64_t)nb * p.out_ld;
+        for (int e0 = 0; e0 < nvec; e0 += 4 * 128) {
+          float4 rv[4], av[4];
+          int64_t off[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 128 + etid;
+            ok[u] = e < nvalid;
+            const int row = (int)(((uint32_t)e * vpr_magic) >> 16);
+            const int c4 = e - row * vpr;
+            off[u] = blkbase + (int64_t)row * p.out_ld + c4 * 4;
+            rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            av[u] = rv[u];
+            if (ok[u] && p.res) rv[u] = *reinterpret_cast<const float4*>(p.res + off[u]);
+            if (ok[u] && p.accum) av[u] = *reinterpret_cast<const float4*>(p.accum + off[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            const int e = e0 + u * 128 + etid;
+            const int row = (int)(((uint32_t)e * vpr_magic) >> 16);
+            const int c4 = e - row * vpr;
+            const float4 d = *reinterpret_cast<const float4*>(sbuf + e * 4);
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c4 * 4));
+            float4 y;
+            y.x = (d.x + bv.x + rv[u].x) * p.scale + av[u].x;
+            y.y = (d.y + bv.y + rv[u].y) * p.scale + av[u].y;
+            y.z = (d.z + bv.z + rv[u].z) * p.scale + av[u].z;
+            y.w = (d.w + bv.w + rv[u].w) * p.scale + av[u].w;
+            if (p.out_bf16) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[u]) = pk;
+            } else {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off[u]) = y;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[acc]);
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
   }

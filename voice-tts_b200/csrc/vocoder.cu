@@ -71,7 +71,7 @@ struct bvg_vocoder {
   void* dev_wav = nullptr;  size_t dev_wav_bytes = 0;
   int last_launches = 0;
   // per-kernel CUDA-event profiling (option "profile"): category -> accumulated work; events resolved on read
-  struct ProfRec { int cat; double work; cudaEvent_t e0, e1; };
+  struct ProfRec { int cat; double work; cudaEvent_t e0, e1; int cin, cout, k, dil; long long rows; };
   int opt_profile = 0;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -173,11 +173,15 @@ static cudaEvent_t prof_event(bvg_vocoder* v) {
 }
 struct ProfScope {
   bvg_vocoder* v; cudaStream_t st; int cat; double work; cudaEvent_t e0 = nullptr;
+  int cin = 0, cout = 0, k = 0, dil = 0; long long rows = 0;
   ProfScope(bvg_vocoder* v_, cudaStream_t st_, int cat_, double work_) : v(v_), st(st_), cat(cat_), work(work_) {
     if (v->opt_profile) { e0 = prof_event(v); cudaEventRecord(e0, st); }
   }
   ~ProfScope() {
-    if (e0) { cudaEvent_t e1 = prof_event(v); cudaEventRecord(e1, st); v->prof.push_back({cat, work, e0, e1}); }
+    if (e0) {
+      cudaEvent_t e1 = prof_event(v); cudaEventRecord(e1, st);
+      v->prof.push_back({cat, work, e0, e1, cin, cout, k, dil, rows});
+    }
   }
 };
 
@@ -195,6 +199,7 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
   }
   // algorithmic flops: 2*Cout*Cin*k*T_out*B (Conv1d) / 2*Cin*Cout*k*T_in*B (ConvTranspose1d), unpadded channels
   ProfScope ps(v, st, umma ? CAT_CONV_UMMA : CAT_CONV_SIMT, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
+  ps.cin = c.Cin; ps.cout = c.up > 0 ? -c.Cout : c.Cout; ps.k = c.k_torch; ps.dil = c.dil; ps.rows = (long long)B * T;
   return umma ? conv_umma_launch(a, v->opt_umma_variant, st) : conv_simt_launch(a, st);
 }
 
@@ -203,6 +208,7 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   const bool fast = v->opt_fast_sin >= 0 ? v->opt_fast_sin != 0 : v->cfg.mode == BVG_MODE_BF16;
   // algorithmic bytes: one read + one write of the unpadded tensor
   ProfScope ps(v, st, CAT_ACT, (double)B * T * a.C * (dtype_size(in_dt) + dtype_size(out_dt)));
+  ps.cin = a.C; ps.cout = a.C; ps.k = (int)dtype_size(in_dt); ps.dil = (int)dtype_size(out_dt); ps.rows = (long long)B * T;
   return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, a.Cp, in_dt, out_dt, fast, st);
 }
 
@@ -643,6 +649,24 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
   else if (!strcmp(key, "workspace_mb")) v->opt_ws_cap_mb = value;
   else if (!strcmp(key, "profile")) v->opt_profile = value;
   else BVG_FAIL(BVG_EINVAL, "bvg_set_option: unknown option '%s'", key);
+  return BVG_OK;
+}
+
+// Debug: one line per recorded launch (category, shape, ms, achieved rate) to `path`; does not clear.
+extern "C" int bvg_profile_dump(bvg_vocoder* v, const char* path) {
+  if (!v || !path) BVG_FAIL(BVG_EINVAL, "bvg_profile_dump: bad argument");
+  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  BVG_CUDA(cudaDeviceSynchronize());
+  FILE* f = fopen(path, "w");
+  if (!f) BVG_FAIL(BVG_EINVAL, "cannot open %s", path);
+  fprintf(f, "cat,cin,cout,k,dil,rows,ms,work,rate\n");
+  for (auto& r : v->prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    fprintf(f, "%d,%d,%d,%d,%d,%lld,%.4f,%.4g,%.4g\n", r.cat, r.cin, r.cout, r.k, r.dil, r.rows, t, r.work,
+            t > 0 ? r.work / (t * 1e-3) : 0.0);
+  }
+  fclose(f);
   return BVG_OK;
 }
 
