@@ -13,7 +13,9 @@
 //   y[t]    = sum_k down[k] * v[clamp(2t+k-5, 0, 2T-1)]
 // reference: alias_free_activation/torch/{resample.py:29-38,55-58, filter.py:94-101, act.py:25-30},
 //            activations.py:107-120.
-#include "common.cuh"
+#include <cstring>
+
+#include "act_packed.cuh"
 
 namespace bvg {
 
@@ -59,21 +61,23 @@ struct VecIO<__nv_bfloat16, 2> {
 // One time step of the sliding window for VEC channels.  S is the step index
 // modulo 6 (compile time after unrolling): slot (S+5)%6 of X receives x[t+5],
 // slots (2S+10)%12,(2S+11)%12 of V receive v[2t+5], v[2t+6].
+// The arithmetic (operation order, fma/mul placement) is bit-identical to the packed
+// kernel's, so the result does not depend on how a tensor is cut into segments.
 #define BVG_ACT_UP(S, X, taps, a, ib, vo, ve)                              \
   _Pragma("unroll") for (int j = 0; j < VEC; ++j) {                        \
-    float uo = 0.f, ue = 0.f;                                              \
+    float uo = snake_acc_init<FAST>(ib[j]), ue = uo;                       \
     _Pragma("unroll") for (int q = 0; q < 6; ++q) {                        \
       const float xv = X[((S) + 5 - q) % 6][j];                            \
       uo = fmaf(taps.up[2 * q], xv, uo);                                   \
       ue = fmaf(taps.up[2 * q + 1], xv, ue);                               \
     }                                                                      \
-    vo[j] = snake_eval<FAST>(uo, a[j], ib[j]);                             \
-    ve[j] = snake_eval<FAST>(ue, a[j], ib[j]);                             \
+    vo[j] = snake_apply<FAST>(uo, a[j], ib[j]);                            \
+    ve[j] = snake_apply<FAST>(ue, a[j], ib[j]);                            \
   }
 #define BVG_ACT_DOWN(S, V, taps, y)                                        \
   _Pragma("unroll") for (int j = 0; j < VEC; ++j) {                        \
-    float acc = 0.f;                                                       \
-    _Pragma("unroll") for (int k = 0; k < 12; ++k)                         \
+    float acc = taps.down[0] * V[(2 * (S)) % 12][j];                       \
+    _Pragma("unroll") for (int k = 1; k < 12; ++k)                         \
       acc = fmaf(taps.down[k], V[(2 * (S) + k) % 12][j], acc);             \
     y[j] = acc;                                                            \
   }
@@ -82,7 +86,9 @@ template <typename Tin, typename Tout, int VEC, bool FAST>
 __global__ void __launch_bounds__(128)
 act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
                 const float* __restrict__ beta_log, const Taps taps, int B, int64_t T, int C, int L,
-                int nseg, int64_t nitems) {
+                int nseg, int nseg_head, int64_t tail_start, int64_t nitems) {
+  // this launch covers `nseg` segments of length L per utterance: `nseg_head` segments from
+  // row 0 and the rest from row `tail_start` (the rows in between belong to the packed kernel)
   const int P = C / VEC;
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= nitems) return;
@@ -101,15 +107,17 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
 
   const Tin* sp = src + (int64_t)b * T * C + c0;
   Tout* dp = dst + (int64_t)b * T * C + c0;
-  const int64_t t0 = (int64_t)seg * L;
-  const int64_t t1 = (t0 + L < T) ? t0 + L : T;
+  const bool head = seg < nseg_head;
+  const int64_t t0 = head ? (int64_t)seg * L : tail_start + (int64_t)(seg - nseg_head) * L;
+  const int64_t rend = head ? (tail_start < T ? tail_start : T) : T;   // end of this segment's region
+  const int64_t t1 = (t0 + L < rend) ? t0 + L : rend;
   const int64_t tlast = T - 1;
 
   float X[6][VEC];    // slot p holds x at time == p (mod 6) relative to the first step
   float V[12][VEC];   // slot p holds v at index == p (mod 12) relative to the first step
 
   // steps run over t = t0-5 .. t1-1; step t loads x[t+5] and produces v[2t+5], v[2t+6], y[t].
-  if (t0 >= 5 && t0 + L + 4 <= tlast) {
+  if (t0 >= 5 && t0 + L + 4 <= tlast && t1 - t0 == L) {
     // ---- interior segment (L = 6n-5): no clamps, no edge fixes, no predicates ----
     const Tin* lp = sp + (t0 - 5) * C;
     Tout* op = dp + t0 * C;
@@ -201,15 +209,135 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed variant (2 channels per thread as one f32x2 lane pair): Blackwell's FFMA2
+// (fma.rn.f32x2) does two FMAs per issue slot.  ncu showed the scalar kernel is
+// issue-bound (issue-active ~80 %, 45 lane-instructions per element); packing the two
+// channel FIRs halves the FMA issue count (-> ~23 per element).
+//   taps are passed pre-duplicated {f,f}; by symmetry f[k] = f[11-k] only 6 distinct
+//   pairs per filter are needed: up[2q] = U[q], up[2q+1] = U[5-q], down[k] = D[min(k,11-k)].
+//   fast snake: v = (u + hb) - hb*cos(2a*u) with the FIR accumulator initialised to hb,
+//   so u + hb is free and 2a*u = fma(2a, u + hb, -2a*hb).
+template <typename T> struct PairIO;
+template <> struct PairIO<float> {
+  typedef float2 raw_t;
+  static __device__ __forceinline__ raw_t ldraw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ f32x2 cvt(raw_t r) { return pk2(r.x, r.y); }
+  static __device__ __forceinline__ void store(float* p, f32x2 v) {
+    float a, b; upk2(v, a, b);
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+  }
+};
+template <> struct PairIO<__nv_bfloat16> {
+  typedef uint32_t raw_t;
+  static __device__ __forceinline__ raw_t ldraw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ f32x2 cvt(raw_t r) { return pk2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, f32x2 v) {
+    float a, b; upk2(v, a, b);
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+  }
+};
+
+#define BVG_ACT2_STEP(S, WITH_DOWN)                                                        \
+  {                                                                                        \
+    f32x2 uo = sn.acc_init(), ue = uo;                                                     \
+    _Pragma("unroll") for (int q = 0; q < 6; ++q) {                                        \
+      const f32x2 xv = X[((S) + 5 - q) % 6];                                               \
+      uo = fma2(tp.u[q], xv, uo);                                                          \
+      ue = fma2(tp.u[5 - q], xv, ue);                                                      \
+    }                                                                                      \
+    V[(2 * (S) + 10) % 12] = sn.apply(uo);                                                 \
+    V[(2 * (S) + 11) % 12] = sn.apply(ue);                                                 \
+    if (WITH_DOWN) {                                                                       \
+      f32x2 acc = mul2(tp.d[0], V[(2 * (S)) % 12]);                                        \
+      _Pragma("unroll") for (int k = 1; k < 12; ++k)                                       \
+        acc = fma2(tp.d[k < 6 ? k : 11 - k], V[(2 * (S) + k) % 12], acc);                  \
+      PairIO<Tout>::store(op, acc);                                                        \
+      op += C;                                                                             \
+    }                                                                                      \
+  }
+
+// interior segments only (t0 >= 5, t0 + L + 4 <= T - 1, L = 6n-5); edge segments are
+// handled by the scalar kernel's generic path in a second (tiny) launch.
+template <typename Tin, typename Tout, bool FAST>
+__global__ void __launch_bounds__(128)
+act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
+                       const float* __restrict__ beta_log, const TapsPacked tp, int B, int64_t T, int C, int L,
+                       int nseg_int, int head_len, int64_t nitems) {
+  const int P = C / 2;
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= nitems) return;
+  const int pair = (int)(item % P);
+  const int64_t rest = item / P;
+  const int seg = (int)(rest % nseg_int);
+  const int b = (int)(rest / nseg_int);
+  const int c0 = pair * 2;
+  SnakePair<FAST> sn;
+  sn.init(__ldg(alpha_log + c0), __ldg(alpha_log + c0 + 1), __ldg(beta_log + c0), __ldg(beta_log + c0 + 1));
+
+  const int64_t t0 = head_len + (int64_t)seg * L;   // interior region [head_len, head_len + nseg_int*L)
+  const Tin* lp = src + ((int64_t)b * T + (t0 - 5)) * C + c0;
+  Tout* op = dst + ((int64_t)b * T + t0) * C + c0;
+
+  f32x2 X[6], V[12];
+  typename PairIO<Tin>::raw_t XC[6], XN[6];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { X[i] = PairIO<Tin>::cvt(PairIO<Tin>::ldraw(lp)); lp += C; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { XC[i] = PairIO<Tin>::ldraw(lp); lp += C; }
+  const int nbody = (L + 5) / 6;   // L = 6n-5 -> n bodies of 6 steps; the first has 5 warm-up steps
+  // software pipeline: the loads of body i+1 are in flight while body i is computed
+  if (nbody > 1) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { XN[i] = PairIO<Tin>::ldraw(lp); lp += C; }
+  }
+#pragma unroll
+  for (int s = 0; s < 6; ++s) {
+    X[(s + 5) % 6] = PairIO<Tin>::cvt(XC[s]);
+    if (s < 5) BVG_ACT2_STEP(s, false) else BVG_ACT2_STEP(s, true)
+  }
+  for (int it = 1; it < nbody; ++it) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) XC[i] = XN[i];
+    if (it + 1 < nbody) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { XN[i] = PairIO<Tin>::ldraw(lp); lp += C; }
+    }
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      X[(s + 5) % 6] = PairIO<Tin>::cvt(XC[s]);
+      BVG_ACT2_STEP(s, true)
+    }
+  }
+}
+
+// Launch plan: rows [kEdge, kEdge + n_int*L) of every utterance ("interior": no clamps, no edge
+// rules) go to the packed FFMA2 kernel in segments of L = 6n-5 rows; the head [0, kEdge) and the
+// tail go to the scalar edge-aware kernel in SHORT segments (13 rows) so that the few edge
+// threads are not a serial tail behind the main kernel.
 template <typename Tin, typename Tout, bool FAST>
 static int launch_cl(void* dst, const void* src, const float* alpha_log, const float* beta_log,
                      const Taps& taps, int B, int64_t T, int C, cudaStream_t st) {
-  // segment length L = 6n-5 keeps the 6-step unrolled body full; pick the longest
-  // one that still gives >= ~4 waves of 128-thread blocks on 148 SMs.
   const bool vec2 = (C % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) % (2 * sizeof(Tin))) == 0) &&
                     ((reinterpret_cast<uintptr_t>(dst) % (2 * sizeof(Tout))) == 0);
-  const int VECr = vec2 ? 2 : 1;
-  const int64_t P = C / VECr;
+  const int threads = 128;
+  constexpr int kEdge = 13;   // 6n-5, >= 5
+  if (!vec2) {
+    // odd channel count / unaligned: scalar kernel over everything
+    static const int kSegLens[] = {253, 127, 61, 31, 13};
+    int L = kSegLens[4];
+    for (int i = 0; i < 5; ++i)
+      if ((int64_t)B * ceil_div(T, kSegLens[i]) * C >= 148LL * 16 * 128) { L = kSegLens[i]; break; }
+    const int nseg = (int)ceil_div(T, L);
+    const int64_t nitems = (int64_t)B * nseg * C;
+    const int64_t blocks = ceil_div(nitems, threads);
+    if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
+    act1d_cl_kernel<Tin, Tout, 1, FAST><<<(unsigned)blocks, threads, 0, st>>>(
+        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, L, nseg, nseg, T, nitems);
+    BVG_LAUNCHED();
+    return BVG_OK;
+  }
+  const int64_t P = C / 2;
   static const int kSegLens[] = {253, 127, 61, 31, 13};  // all of the form 6n-5
   const int64_t want_items = 148LL * 16 * 128;
   int L = kSegLens[4];
@@ -219,18 +347,31 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
       break;
     }
   }
-  const int nseg = (int)ceil_div(T, L);
+  // interior segments: kEdge + s*L + L + 4 <= T - 1
+  int64_t n_int = (T - 5 - kEdge) / L;
+  if (n_int < 0) n_int = 0;
+  if (n_int > 0) {
+    TapsPacked tp;
+    make_taps_packed(&tp, taps);
+    const int64_t nitems = (int64_t)B * n_int * P;
+    const int64_t blocks = ceil_div(nitems, threads);
+    if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
+    act1d_cl_packed_kernel<Tin, Tout, FAST><<<(unsigned)blocks, threads, 0, st>>>(
+        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, L, (int)n_int, kEdge, nitems);
+    BVG_LAUNCHED();
+  }
+  // edges: head [0, kEdge) (or everything when there is no interior) and tail [tail_start, T)
+  const int64_t tail_start = n_int > 0 ? kEdge + n_int * L : T;
+  const int64_t head_end = n_int > 0 ? kEdge : T;
+  const int nseg_head = (int)ceil_div(head_end, kEdge);
+  const int nseg_tail = (int)ceil_div(T - tail_start, kEdge);
+  const int nseg = nseg_head + nseg_tail;
   const int64_t nitems = (int64_t)B * nseg * P;
-  const int threads = 128;
   const int64_t blocks = ceil_div(nitems, threads);
   if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
-  if (vec2) {
-    act1d_cl_kernel<Tin, Tout, 2, FAST><<<(unsigned)blocks, threads, 0, st>>>(
-        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, L, nseg, nitems);
-  } else {
-    act1d_cl_kernel<Tin, Tout, 1, FAST><<<(unsigned)blocks, threads, 0, st>>>(
-        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, L, nseg, nitems);
-  }
+  act1d_cl_kernel<Tin, Tout, 2, FAST><<<(unsigned)blocks, threads, 0, st>>>(
+      (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, kEdge, nseg, nseg_head,
+      n_int > 0 ? tail_start : T, nitems);
   BVG_LAUNCHED();
   return BVG_OK;
 }
