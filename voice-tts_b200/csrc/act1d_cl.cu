@@ -280,32 +280,30 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
   Tout* op = dst + ((int64_t)b * T + t0) * C + c0;
 
   f32x2 X[6], V[12];
-  typename PairIO<Tin>::raw_t XC[6], XN[6];
+  // Rolling prefetch: R[s] holds the raw row consumed by step s of the current 12-step
+  // iteration; right after it is consumed the slot is refilled with the row 12 steps ahead, so
+  // every load has 12 steps (~2-3k cycles) to land.  The launcher keeps 12 spare rows behind the
+  // interior region, so the run-ahead loads of the last segment stay inside the tensor.
+  typename PairIO<Tin>::raw_t R[12];
 #pragma unroll
   for (int i = 0; i < 5; ++i) { X[i] = PairIO<Tin>::cvt(PairIO<Tin>::ldraw(lp)); lp += C; }
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { XC[i] = PairIO<Tin>::ldraw(lp); lp += C; }
-  const int nbody = (L + 5) / 6;   // L = 6n-5 -> n bodies of 6 steps; the first has 5 warm-up steps
-  // software pipeline: the loads of body i+1 are in flight while body i is computed
-  if (nbody > 1) {
+  for (int i = 0; i < 12; ++i) { R[i] = PairIO<Tin>::ldraw(lp); lp += C; }
+  const int niter = (L + 5) / 12;   // L = 12m-5
+  // first iteration: steps 0..4 are warm-up (no output)
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { XN[i] = PairIO<Tin>::ldraw(lp); lp += C; }
-  }
-#pragma unroll
-  for (int s = 0; s < 6; ++s) {
-    X[(s + 5) % 6] = PairIO<Tin>::cvt(XC[s]);
+  for (int s = 0; s < 12; ++s) {
+    X[(s + 5) % 6] = PairIO<Tin>::cvt(R[s]);
+    R[s] = PairIO<Tin>::ldraw(lp);
+    lp += C;
     if (s < 5) BVG_ACT2_STEP(s, false) else BVG_ACT2_STEP(s, true)
   }
-  for (int it = 1; it < nbody; ++it) {
+  for (int it = 1; it < niter; ++it) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) XC[i] = XN[i];
-    if (it + 1 < nbody) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { XN[i] = PairIO<Tin>::ldraw(lp); lp += C; }
-    }
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      X[(s + 5) % 6] = PairIO<Tin>::cvt(XC[s]);
+    for (int s = 0; s < 12; ++s) {
+      X[(s + 5) % 6] = PairIO<Tin>::cvt(R[s]);
+      R[s] = PairIO<Tin>::ldraw(lp);
+      lp += C;
       BVG_ACT2_STEP(s, true)
     }
   }
@@ -338,7 +336,7 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
     return BVG_OK;
   }
   const int64_t P = C / 2;
-  static const int kSegLens[] = {253, 127, 61, 31, 13};  // all of the form 6n-5
+  static const int kSegLens[] = {247, 127, 55, 31, 19};  // all of the form 12m-5
   const int64_t want_items = 148LL * 16 * 128;
   int L = kSegLens[4];
   for (int i = 0; i < 5; ++i) {
@@ -347,8 +345,8 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
       break;
     }
   }
-  // interior segments: kEdge + s*L + L + 4 <= T - 1
-  int64_t n_int = (T - 5 - kEdge) / L;
+  // interior segments: kEdge + s*L + L + 4 + 12 (prefetch run-ahead) <= T - 1
+  int64_t n_int = (T - 5 - 12 - kEdge) / L;
   if (n_int < 0) n_int = 0;
   if (n_int > 0) {
     TapsPacked tp;

@@ -21,9 +21,7 @@
 //   warps 2-5 : epilogue: tcgen05.ld -> (+bias, +residual, *scale, +accum) -> coalesced global stores
 //
 // reference semantics: torch Conv1d/ConvTranspose1d as built in bigvgan.py:59-66,76-83,285-287,306-312.
-#include <cuda.h>
-
-#include "conv.cuh"
+#include "umma_common.cuh"
 
 namespace bvg {
 
@@ -57,19 +55,6 @@ struct UmmaParams {
   int64_t n_tiles;   // B * n_ttiles * n_cotiles
   int base_mode;     // debug: 1 = put (addr>>7)&7 into the descriptor base_offset field
 };
-
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes, int base_mode) {
-  // K-major, swizzled: SBO = 8 rows; LBO unused (1); version 1 (sm_100)
-  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  if (base_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
 
 template <bool PER_TAP_X>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -153,52 +138,58 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------ MMA issuer
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) |
-                             ((uint32_t)(UM_M >> 4) << 24);
-      uint32_t as = 0, aph = 0, xs = 0, xph = 0, acc = 0, accph = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait(&t_empty[acc], accph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.NT;
-        uint32_t first = 1;
-        for (int c = 0; c < p.nchunks; ++c) {
-          if (!PER_TAP_X) {
+    // ------------------------------------------------ MMA issuer: the whole warp walks the loop with
+    // warp-uniform values (descriptors stay in uniform registers); one elected lane issues.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) |
+                           ((uint32_t)(UM_M >> 4) << 24);
+    // descriptor template once; per MMA only the start-address field (addr >> 4) advances
+    const uint64_t desc0 = make_smem_desc(0, row_bytes, 0);
+    const uint32_t tap_step = (uint32_t)(p.dil * row_bytes) >> 4;
+    const int nkk = p.KC / 16;
+    const uint32_t a_base = smem_u32(a_st), x_base = smem_u32(x_st);
+    uint32_t as = 0, aph = 0, xs = 0, xph = 0, acc = 0, accph = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(&t_empty[acc], accph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.NT;
+      uint32_t first = 1;
+      for (int c = 0; c < p.nchunks; ++c) {
+        if (!PER_TAP_X) {
+          mbar_wait(&x_full[xs], xph);
+          tc_fence_after();
+        }
+        for (int j = 0; j < ntaps; ++j) {
+          if (PER_TAP_X) {
             mbar_wait(&x_full[xs], xph);
             tc_fence_after();
           }
-          for (int j = 0; j < ntaps; ++j) {
-            if (PER_TAP_X) {
-              mbar_wait(&x_full[xs], xph);
-              tc_fence_after();
-            }
-            mbar_wait(&a_full[as], aph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_st + as * UM_A_STAGE_BYTES);
-            uint32_t x_addr = smem_u32(x_st + xs * UM_X_STAGE_BYTES);
-            if (!PER_TAP_X) x_addr += (uint32_t)(j * p.dil) * row_bytes;
-            for (int kk = 0; kk < p.KC / 16; ++kk) {
-              const uint64_t da = make_smem_desc(a_addr + kk * 32, row_bytes, p.base_mode);
-              const uint64_t db = make_smem_desc(x_addr + kk * 32, row_bytes, p.base_mode);
-              umma_f16_ss(d_tmem, da, db, idesc, first ? 0u : 1u);
-              first = 0;
-            }
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint64_t da0 = desc0 + ((a_base + as * UM_A_STAGE_BYTES) >> 4);
+          uint64_t db0 = desc0 + ((x_base + xs * UM_X_STAGE_BYTES) >> 4);
+          if (!PER_TAP_X) db0 += (uint32_t)j * tap_step;
+          if (elect_one()) {
+            umma_f16_ss(d_tmem, da0, db0, idesc, first ? 0u : 1u);
+            for (int kk = 1; kk < nkk; ++kk) umma_f16_ss(d_tmem, da0 + 2 * kk, db0 + 2 * kk, idesc, 1u);
             umma_commit(&a_empty[as]);
-            if (++as == UM_A_STAGES) { as = 0; aph ^= 1; }
-            if (PER_TAP_X) {
-              umma_commit(&x_empty[xs]);
-              if (++xs == UM_X_STAGES) { xs = 0; xph ^= 1; }
-            }
+            if (PER_TAP_X) umma_commit(&x_empty[xs]);
           }
-          if (!PER_TAP_X) {
-            umma_commit(&x_empty[xs]);
+          __syncwarp();
+          first = 0;
+          if (++as == UM_A_STAGES) { as = 0; aph ^= 1; }
+          if (PER_TAP_X) {
             if (++xs == UM_X_STAGES) { xs = 0; xph ^= 1; }
           }
         }
-        umma_commit(&t_full[acc]);
-        if (++acc == 2) { acc = 0; accph ^= 1; }
+        if (!PER_TAP_X) {
+          if (elect_one()) umma_commit(&x_empty[xs]);
+          __syncwarp();
+          if (++xs == UM_X_STAGES) { xs = 0; xph ^= 1; }
+        }
       }
+      if (elect_one()) umma_commit(&t_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; accph ^= 1; }
     }
   } else {
     // -------------------------------------------------- epilogue warps 2..5
@@ -221,7 +212,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int vpr = cv >> 2;                                             // float4 vectors per time row
       const uint32_t vpr_magic = (65536u + (uint32_t)vpr - 1) / (uint32_t)vpr;  // e / vpr for e < 4096
       const bool warp_has_rows = g * 32 < cv;
-      const int nvec = 32 * vpr;                                           // vectors per 32-column block
       const int64_t tilebase = ((int64_t)b * p.T + t0) * p.out_ld + co0;
 
       mbar_wait(&t_full[acc], accph);
@@ -229,28 +219,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * (uint32_t)p.NT;
       int nb_end = p.T - t0;                                               // valid time rows in this tile
       if (nb_end > p.NT) nb_end = p.NT;
-      for (int nb = 0; nb < nb_end; nb += 32, ++blk) {
+      // columns staged per barrier round: the staging buffer holds 4096 floats, so layers with
+      // few valid channels stage up to 128 time columns at once (fewer barrier + residual-latency
+      // round trips per tile: 2 instead of 8 for the 32-channel stage)
+      int cb = (128 / cv) * 32;
+      cb = cb < 32 ? 32 : (cb > 128 ? 128 : cb);
+      for (int nb = 0; nb < nb_end; nb += cb, ++blk) {
         float* sbuf = epi_st + (blk & 1) * (UM_EPI_BUF_BYTES / 4);
+        int cols_here = nb_end - nb;
+        if (cols_here > cb) cols_here = cb;
         if (warp_has_rows) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + nb, v);
-          tmem_ld_wait();
           const int col = g * 32 + lane;
-          if (col < cv) {   // cv is a multiple of 16: the last warp with rows may be half valid
+          for (int sub = 0; sub < cols_here; sub += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + nb + sub, v);
+            tmem_ld_wait();
+            if (col < cv) {   // cv is a multiple of 16: the last warp with rows may be half valid
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sbuf[i * cv + col] = __uint_as_float(v[i]);
+              for (int i = 0; i < 32; ++i) sbuf[(sub + i) * cv + col] = __uint_as_float(v[i]);
+            }
           }
         }
-        if (nb + 32 >= nb_end) {           // all TMEM reads of this tile are done: hand the accumulator back
+        if (nb + cb >= nb_end) {           // all TMEM reads of this tile are done: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[acc]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int rows_here = (nb_end - nb) < 32 ? (nb_end - nb) : 32;
-        const int nvalid = rows_here * vpr;
+        const int nvec = cb * vpr;
+        const int nvalid = cols_here * vpr;
         const int64_t blkbase = tilebase + (int64_t)nb * p.out_ld;
-        for (int e0 = 0; e0 < nvec; e0 += 4 * 128) {
+        for (int e0 = 0; e0 < nvec && e0 < nvalid; e0 += 4 * 128) {
           float4 rv[4], av[4];
           int64_t off[4];
           bool ok[4];
@@ -320,13 +319,20 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
-                       uint32_t b1, int row_bytes) {
+// 3-D bf16 tensor map {d0 (fastest), d1, d2}, box {b0, b1, 1}, swizzle chosen by the box row bytes
+int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                int row_bytes) {
+  return make_map_4d_w(m, base, d0, d1, d2, b0, b1, 1, row_bytes);
+}
+
+// same with a box that is `b2` deep in the slowest dimension (several taps per TMA copy)
+int make_map_4d_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                  uint32_t b2, int row_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) BVG_FAIL(BVG_ENODEV, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -340,6 +346,16 @@ static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
   return BVG_OK;
 }
 
+int umma_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
 bool conv_umma_supported(const ConvArgs& a) {
   if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16) return false;
   if (a.Cin_p % 16 != 0 || a.Cout_r % UM_M != 0) return false;
@@ -349,11 +365,10 @@ bool conv_umma_supported(const ConvArgs& a) {
   return true;
 }
 
-static int g_sm_count = 0;
-
 int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   if (a.B <= 0 || a.T <= 0) return BVG_OK;
   if (!conv_umma_supported(a)) BVG_FAIL(BVG_EINVAL, "conv_umma: unsupported layer shape/dtype");
+  if (a.Cout_n <= 128 && !(variant & 4) && conv_umma_t_fits(a)) return conv_umma_t_launch(a, variant, st);   // time-major variant
   UmmaParams p;
   p.bias = a.bias; p.out = a.out; p.res = a.res; p.accum = a.accum; p.scale = a.scale;
   p.out_bf16 = a.out_dtype == BVG_BF16;
@@ -379,11 +394,7 @@ int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   rc = make_map_3d(&mw, a.w, (uint64_t)a.Cin_p, (uint64_t)a.Cout_r, (uint64_t)a.k, (uint32_t)p.KC, UM_M, row_bytes);
   if (rc) return rc;
 
-  if (g_sm_count == 0) {
-    int dev = 0;
-    BVG_CUDA(cudaGetDevice(&dev));
-    BVG_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_sm_count = umma_sm_count();
   BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
   BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_BYTES));
   const unsigned grid = (unsigned)(p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count);

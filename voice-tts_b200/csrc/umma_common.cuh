@@ -1,0 +1,31 @@
+// Pieces shared by the two tcgen05 conv kernels (channel-major conv_umma.cu, time-major conv_umma_t.cu).
+#pragma once
+#include <cuda.h>
+
+#include "conv.cuh"
+
+namespace bvg {
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes, int base_mode) {
+  // K-major, swizzled: SBO = 8 rows; LBO unused (1); version 1 (sm_100)
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+
+int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                int row_bytes);
+int make_map_4d_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                  uint32_t b2, int row_bytes);
+int umma_sm_count();
+int conv_umma_t_launch(const ConvArgs& a, int variant, cudaStream_t st);
+bool conv_umma_t_fits(const ConvArgs& a);
+
+}  // namespace bvg
