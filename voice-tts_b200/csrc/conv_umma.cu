@@ -201,7 +201,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int etid = (warp - 2) * 32 + lane;   // 0..127 among the epilogue threads
     uint32_t acc = 0, accph = 0;
     uint32_t blk = 0;                     // running 32-column block counter -> staging buffer parity
+    // fire-and-forget L2 prefetch of one tile's residual / accumulate rows (issued one tile ahead)
+    auto prefetch_tile = [&](int64_t tile) {
+      if (!p.res && !p.accum) return;
+      const int cot = (int)(tile % p.n_cotiles);
+      const int64_t r = tile / p.n_cotiles;
+      const int tt = (int)(r % p.n_ttiles);
+      const int b = (int)(r / p.n_ttiles);
+      const int t0 = tt * p.NT;
+      const int co0 = cot * UM_M;
+      const int cv = (p.Cout_n - co0) < UM_M ? (p.Cout_n - co0) : UM_M;
+      int rows = p.T - t0;
+      if (rows > p.NT) rows = p.NT;
+      const int lpr = (cv * 4 + 127) / 128;                  // 128-byte lines per row segment
+      const int64_t base = ((int64_t)b * p.T + t0) * p.out_ld + co0;
+      for (int i = etid; i < rows * lpr; i += 128) {
+        const int row = i / lpr, ln = i - row * lpr;
+        const int64_t off = base + (int64_t)row * p.out_ld + ln * 32;
+        if (p.res) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + off));
+        if (p.accum) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.accum + off));
+      }
+    };
+    if ((int64_t)blockIdx.x < p.n_tiles) prefetch_tile(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      if (tile + gridDim.x < p.n_tiles) prefetch_tile(tile + gridDim.x);
       const int cot = (int)(tile % p.n_cotiles);
       const int64_t r = tile / p.n_cotiles;
       const int tt = (int)(r % p.n_ttiles);

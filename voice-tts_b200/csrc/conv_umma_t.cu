@@ -23,11 +23,12 @@
 
 namespace bvg {
 
-constexpr int UT_THREADS = 192;
+constexpr int UT_EPI_WARPS = 8;                       // two epilogue warps per TMEM lane group
+constexpr int UT_THREADS = 64 + 32 * UT_EPI_WARPS;
 constexpr int UT_W_STAGES = 4;                        // streaming mode: ring of tap groups
-constexpr int UT_X_STAGES = 2;
+constexpr int UT_X_STAGES_MAX = 4;                    // activation-tile ring depth (2..4, by smem budget)
 constexpr int UT_X_STAGE_MAX = 48 * 1024;             // activation tile budget per stage
-constexpr int UT_SCRATCH_BYTES = 4 * 32 * 32 * 4;     // per-warp 32x32 fp32 transpose scratch
+constexpr int UT_SCRATCH_BYTES = UT_EPI_WARPS * 32 * 32 * 4;   // per-warp 32x32 fp32 transpose scratch
 constexpr int UT_SMEM_MAX = 226 * 1024;
 constexpr int UT_W_RESIDENT_MAX = 110 * 1024;         // weights of a whole layer stay in smem below this
 
@@ -51,12 +52,14 @@ struct UmmaTParams {
   int tps;                    // streaming mode: taps per ring stage (one TMA box {KC, N, tps})
   int wtile_bytes;            // N * KC * 2
   int w_region_bytes, x_stage_bytes;
+  int x_stages;               // activation-tile ring depth
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+template <bool RES, bool ACC, bool BF16OUT>
 __global__ void __launch_bounds__(UT_THREADS, 1)
 conv_umma_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const UmmaTParams p) {
@@ -64,14 +67,14 @@ conv_umma_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* w_st = smem;
   unsigned char* x_st = smem + p.w_region_bytes;
-  float* scratch = reinterpret_cast<float*>(x_st + UT_X_STAGES * p.x_stage_bytes);
+  float* scratch = reinterpret_cast<float*>(x_st + p.x_stages * p.x_stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + UT_SCRATCH_BYTES);
   const int w_stage_bytes = p.w_resident ? 0 : p.w_region_bytes / UT_W_STAGES;
   uint64_t* w_full = bars;
   uint64_t* w_empty = w_full + UT_W_STAGES;
   uint64_t* x_full = w_empty + UT_W_STAGES;
-  uint64_t* x_empty = x_full + UT_X_STAGES;
-  uint64_t* t_full = x_empty + UT_X_STAGES;
+  uint64_t* x_empty = x_full + UT_X_STAGES_MAX;
+  uint64_t* t_full = x_empty + UT_X_STAGES_MAX;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
@@ -80,8 +83,8 @@ conv_umma_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < UT_W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < UT_X_STAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < UT_X_STAGES_MAX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], UT_EPI_WARPS); }
     mbar_fence_init();
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
@@ -119,7 +122,7 @@ conv_umma_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           const int trow = t0 - p.center * p.dil;
           for (int bx = 0; bx < p.x_nbox; ++bx)
             tma_load_3d(dstx + bx * xbox_bytes, &tmap_x, c * p.KC, trow + bx * p.x_box_rows, b, &x_full[xs]);
-          if (++xs == UT_X_STAGES) { xs = 0; xph ^= 1; }
+          if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
           if (!p.w_resident) {
             for (int j0 = 0; j0 < p.k; j0 += p.tps) {
               // the box always has tps taps; taps beyond k are zero-filled by TMA (and never used)
@@ -187,23 +190,30 @@ conv_umma_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
         if (elect_one()) umma_commit(&x_empty[xs]);
         __syncwarp();
-        if (++xs == UT_X_STAGES) { xs = 0; xph ^= 1; }
+        if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
       }
       if (elect_one()) umma_commit(&t_full[acc]);
       __syncwarp();
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
   } else {
-    // -------------------------------------------------- epilogue warps 2..5
+    // -------------------------------------------------- epilogue warps 2..9
+    // Two warps per TMEM lane group; the (sub-tile, 32-channel chunk) work items of a tile
+    // alternate between them.  RES / ACC / BF16OUT are compile-time so the per-vector code has
+    // no branches; full 32-row blocks skip the row predicates.
     const int g = warp % 4;                 // TMEM lane group (time rows 32g..32g+31 of each sub-tile)
-    const int etid = (warp - 2) * 32 + lane;
-    float* my = scratch + (warp - 2) * 1024; // this warp's 32x32 transpose scratch
+    const int ew = warp - 2;                // 0..7
+    const int half = ew >> 2;               // which of the two warps of this lane group
+    const int etid = ew * 32 + lane;
+    float* my = scratch + ew * 1024;        // this warp's 32x32 transpose scratch
     const int r8 = lane >> 3, c8 = lane & 7; // transposed role: row 4q + r8, channels 4*c8 .. 4*c8+3 of the chunk
+    const int row_stride = 4 * p.out_ld;    // elements between the rows of consecutive q
+    const int nchunk32 = (p.N + 31) / 32;
     uint32_t acc = 0, accph = 0;
 
     // L2 prefetch of the residual / accumulate rows of one tile (fire and forget)
     auto prefetch_tile = [&](int64_t tile) {
-      if (!p.res && !p.accum) return;
+      if (!RES && !ACC) return;
       const int tt = (int)(tile % p.n_ttiles);
       const int b = (int)(tile / p.n_ttiles);
       const int t0 = tt * p.MT;
@@ -211,9 +221,9 @@ conv_umma_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       if (rows > p.MT) rows = p.MT;
       const int64_t base = ((int64_t)b * p.T + t0) * p.out_ld;
       const int64_t nbytes = (int64_t)rows * p.out_ld * 4;   // rows are contiguous: out_ld == N for these layers
-      for (int64_t o = (int64_t)etid * 128; o < nbytes; o += 128 * 128) {
-        if (p.res) prefetch_l2(reinterpret_cast<const char*>(p.res + base) + o);
-        if (p.accum) prefetch_l2(reinterpret_cast<const char*>(p.accum + base) + o);
+      for (int64_t o = (int64_t)etid * 128; o < nbytes; o += 128 * 32 * UT_EPI_WARPS) {
+        if (RES) prefetch_l2(reinterpret_cast<const char*>(p.res + base) + o);
+        if (ACC) prefetch_l2(reinterpret_cast<const char*>(p.accum + base) + o);
       }
     };
     if ((int64_t)blockIdx.x < p.n_tiles) prefetch_tile(blockIdx.x);
@@ -227,61 +237,62 @@ conv_umma_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       mbar_wait(&t_full[acc], accph);
       tc_fence_after();
       const uint32_t d_base = tmem_base + ((uint32_t)(g * 32) << 16) + acc * (uint32_t)(p.NSUB * p.Np);
-      const int nchunk32 = (p.N + 31) / 32;
-      for (int m = 0; m < p.NSUB; ++m) {
-        const int trow0 = t0 + m * 128 + g * 32;          // first time row of this warp's 32-row block
-        const bool any_rows = trow0 < p.T;
-        for (int cc = 0; cc < nchunk32; ++cc) {
-          const int cvalid = (p.N - cc * 32) < 32 ? (p.N - cc * 32) : 32;   // 16 or 32
-          const bool lane_ok_c = c8 * 4 < cvalid;
-          // residual / accumulate operands first: their latency overlaps the TMEM load + transpose
-          float4 rv[8], av[8];
-          int64_t off[8];
-          bool ok[8];
-          const int64_t rowbase = ((int64_t)b * p.T + trow0) * p.out_ld + cc * 32 + c8 * 4;
+      const int nitems = p.NSUB * nchunk32;
+      for (int w = half; w < nitems; w += 2) {
+        const int m = w / nchunk32, cc = w - m * nchunk32;
+        const int trow0 = t0 + m * 128 + g * 32;            // first time row of this warp's 32-row block
+        const int nrows = p.T - trow0;                       // valid rows from trow0 on (may be <= 0)
+        const int cvalid = p.N - cc * 32;                    // >= 16
+        const bool lane_ok_c = c8 * 4 < cvalid;
+        const bool full = nrows >= 32 && cvalid >= 32;
+        const int64_t e0 = ((int64_t)b * p.T + trow0 + r8) * p.out_ld + cc * 32 + c8 * 4;
+        const float* resp = RES ? p.res + e0 : nullptr;
+        const float* accp = ACC ? p.accum + e0 : nullptr;
+        // residual / accumulate operands first: their latency overlaps the TMEM load + transpose
+        float4 rv[8], av[8];
+        if (RES || ACC) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int rr = 4 * q + r8;
-            ok[q] = any_rows && lane_ok_c && (trow0 + rr) < p.T;
-            off[q] = rowbase + (int64_t)rr * p.out_ld;
-            rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            av[q] = rv[q];
-            if (ok[q] && p.res) rv[q] = *reinterpret_cast<const float4*>(p.res + off[q]);
-            if (ok[q] && p.accum) av[q] = *reinterpret_cast<const float4*>(p.accum + off[q]);
+            const bool ok = full || (lane_ok_c && (4 * q + r8) < nrows);
+            if (RES) rv[q] = ok ? *reinterpret_cast<const float4*>(resp + q * row_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ACC) av[q] = ok ? *reinterpret_cast<const float4*>(accp + q * row_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && lane_ok_c) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc * 32 + c8 * 4));
+        }
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && lane_ok_c) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc * 32 + c8 * 4));
 
-          uint32_t v[32];
-          tmem_ld_32x32(d_base + m * p.Np + cc * 32, v);   // lane = time row, v[i] = channel cc*32+i
-          tmem_ld_wait();
-          // transpose through the warp's scratch: row = lane, 16-byte chunk i stored at chunk (i ^ (lane & 7))
-          __syncwarp();
+        uint32_t v[32];
+        tmem_ld_32x32(d_base + m * p.Np + cc * 32, v);   // lane = time row, v[i] = channel cc*32+i
+        tmem_ld_wait();
+        // transpose through the warp's scratch: row = lane, 16-byte chunk i stored at chunk (i ^ (lane & 7))
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 f = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                   __uint_as_float(v[4 * i + 3]));
-            *reinterpret_cast<float4*>(my + lane * 32 + ((i ^ (lane & 7)) << 2)) = f;
-          }
-          __syncwarp();
+        for (int i = 0; i < 8; ++i) {
+          float4 f = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                 __uint_as_float(v[4 * i + 3]));
+          *reinterpret_cast<float4*>(my + lane * 32 + ((i ^ (lane & 7)) << 2)) = f;
+        }
+        __syncwarp();
+        const float sc = p.scale;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int rr = 4 * q + r8;
-            const float4 d = *reinterpret_cast<const float4*>(my + rr * 32 + ((c8 ^ (rr & 7)) << 2));
-            if (!ok[q]) continue;
-            float4 y;
-            y.x = (d.x + bv.x + rv[q].x) * p.scale + av[q].x;
-            y.y = (d.y + bv.y + rv[q].y) * p.scale + av[q].y;
-            y.z = (d.z + bv.z + rv[q].z) * p.scale + av[q].z;
-            y.w = (d.w + bv.w + rv[q].w) * p.scale + av[q].w;
-            if (p.out_bf16) {
+        for (int q = 0; q < 8; ++q) {
+          const int rr = 4 * q + r8;
+          const float4 d = *reinterpret_cast<const float4*>(my + rr * 32 + ((c8 ^ (rr & 7)) << 2));
+          float4 y;
+          y.x = d.x + bv.x; y.y = d.y + bv.y; y.z = d.z + bv.z; y.w = d.w + bv.w;
+          if (RES) { y.x += rv[q].x; y.y += rv[q].y; y.z += rv[q].z; y.w += rv[q].w; }
+          y.x *= sc; y.y *= sc; y.z *= sc; y.w *= sc;
+          if (ACC) { y.x += av[q].x; y.y += av[q].y; y.z += av[q].z; y.w += av[q].w; }
+          const bool ok = full || (lane_ok_c && rr < nrows);
+          if (ok) {
+            if (BF16OUT) {
               __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
               uint2 pk;
               pk.x = *reinterpret_cast<uint32_t*>(&lo);
               pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[q]) = pk;
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + e0 + q * row_stride) = pk;
             } else {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off[q]) = y;
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e0 + q * row_stride) = y;
             }
           }
         }
@@ -325,7 +336,8 @@ static bool plan_t(const ConvArgs& a, int variant, UmmaTParams& p, int* smem_out
     if (p.tps > p.k) p.tps = p.k;
     p.w_region_bytes = UT_W_STAGES * round_up(p.tps * p.wtile_bytes, 1024);
   }
-  const int x_budget = (UT_SMEM_MAX - 1024 - 256 - UT_SCRATCH_BYTES - p.w_region_bytes) / UT_X_STAGES;
+  const int x_total_budget = UT_SMEM_MAX - 1024 - 256 - UT_SCRATCH_BYTES - p.w_region_bytes;
+  const int x_budget = x_total_budget / 2;
   const int x_cap = x_budget < UT_X_STAGE_MAX ? x_budget : UT_X_STAGE_MAX;
   int nsub = 256 / p.Np;
   if (nsub > 4) nsub = 4;
@@ -338,13 +350,18 @@ static bool plan_t(const ConvArgs& a, int variant, UmmaTParams& p, int* smem_out
   p.x_nbox = (int)ceil_div(xrows, 256);
   p.x_box_rows = round_up((int)ceil_div(xrows, p.x_nbox), 8);
   p.x_stage_bytes = round_up(p.x_nbox * p.x_box_rows * row_bytes, 1024);
-  if (p.x_stage_bytes > x_cap + 1024 || p.x_stage_bytes * UT_X_STAGES + p.w_region_bytes + UT_SCRATCH_BYTES + 1280 > UT_SMEM_MAX)
+  if (p.x_stage_bytes > x_cap + 1024 || p.x_stage_bytes * 2 + p.w_region_bytes + UT_SCRATCH_BYTES + 1280 > UT_SMEM_MAX)
     return false;
+  // deeper activation ring when it fits: the per-tile MMA work of these layers is short, so the
+  // TMA latency of the (narrow-row) activation tile must be hidden by running several tiles ahead
+  p.x_stages = x_total_budget / p.x_stage_bytes;
+  if (p.x_stages > UT_X_STAGES_MAX) p.x_stages = UT_X_STAGES_MAX;
+  if (p.x_stages < 2) p.x_stages = 2;
   p.n_ttiles = (int)ceil_div(a.T, p.MT);
   p.n_tiles = (int64_t)a.B * p.n_ttiles;
   p.base_mode = variant & 1;
   if (a.out_ld != a.Cout_n || a.Cout_n > 128 || a.Cout_n % 16) return false;
-  *smem_out = 1024 + p.w_region_bytes + UT_X_STAGES * p.x_stage_bytes + UT_SCRATCH_BYTES + 256;
+  *smem_out = 1024 + p.w_region_bytes + p.x_stages * p.x_stage_bytes + UT_SCRATCH_BYTES + 256;
   return true;
 }
 
@@ -369,9 +386,24 @@ int conv_umma_t_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   rc = make_map_4d_w(&mw, a.w, (uint64_t)a.Cin_p, (uint64_t)a.Cout_r, (uint64_t)a.k, (uint32_t)p.KC, (uint32_t)p.N,
                      (uint32_t)p.tps, row_bytes);
   if (rc) return rc;
-  BVG_CUDA(cudaFuncSetAttribute(conv_umma_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UT_SMEM_MAX));
   const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
-  conv_umma_t_kernel<<<grid, UT_THREADS, smem_bytes, st>>>(mx, mw, p);
+#define BVG_T_LAUNCH(R, A, O)                                                                                         \
+  do {                                                                                                                \
+    BVG_CUDA(cudaFuncSetAttribute(conv_umma_t_kernel<R, A, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, UT_SMEM_MAX)); \
+    conv_umma_t_kernel<R, A, O><<<grid, UT_THREADS, smem_bytes, st>>>(mx, mw, p);                                     \
+  } while (0)
+  const int sel = (p.res ? 4 : 0) | (p.accum ? 2 : 0) | (p.out_bf16 ? 1 : 0);
+  switch (sel) {
+    case 0: BVG_T_LAUNCH(false, false, false); break;
+    case 1: BVG_T_LAUNCH(false, false, true); break;
+    case 2: BVG_T_LAUNCH(false, true, false); break;
+    case 3: BVG_T_LAUNCH(false, true, true); break;
+    case 4: BVG_T_LAUNCH(true, false, false); break;
+    case 5: BVG_T_LAUNCH(true, false, true); break;
+    case 6: BVG_T_LAUNCH(true, true, false); break;
+    default: BVG_T_LAUNCH(true, true, true); break;
+  }
+#undef BVG_T_LAUNCH
   BVG_LAUNCHED();
   return BVG_OK;
 }
