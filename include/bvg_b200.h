@@ -101,6 +101,14 @@ int bvg_conv1d_fwd(float* dst, const float* src, const float* weight, const floa
 int bvg_convtr1d_fwd(float* dst, const float* src, const float* weight, const float* bias,
                      int B, int Cin, int Cout, int64_t T, int k, int stride, int mode,
                      bvg_stream_t stream);
+/* Conv1d with the AMPBlock1 residual and the resblock mean folded into its epilogue
+ * (bigvgan.py:132-141 `x = xt + x`, :369-375 `xs += ...; x = xs / num_kernels`):
+ *   dst = (conv1d(src) + bias + res) * scale + accum,   res / accum: fp32 [B, Cout, T] or NULL
+ * (accum without res is evaluated by the plain kernels).  out_bf16 != 0 rounds the result to bf16
+ * before it is returned as fp32 (what the next ConvTranspose1d consumes in BVG_MODE_BF16). */
+int bvg_conv1d_res_fwd(float* dst, const float* src, const float* weight, const float* bias, const float* res,
+                       const float* accum, float scale, int out_bf16, int B, int Cin, int Cout, int64_t T, int k,
+                       int dilation, int mode, bvg_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Whole generator.  Build: bvg_create -> bvg_set_tensor for every state-dict

@@ -79,6 +79,51 @@ def test_conv1d_full_size_tcgen05(ops):
     assert (ys - y[:1]).abs().max() <= 2e-5 * float(ys.abs().max())
 
 
+RES_CASES = [  # B, Cin, Cout, T, k, dil, with_accum, out_bf16
+    (1, 24, 24, 700, 3, 1, False, False), (2, 24, 24, 1500, 11, 5, True, False), (1, 48, 48, 900, 7, 3, True, True),
+    (2, 96, 96, 300, 3, 1, False, True), (1, 192, 192, 530, 7, 1, True, False), (1, 384, 384, 300, 3, 5, True, True),
+    (1, 32, 80, 257, 3, 1, False, False), (3, 16, 16, 33, 3, 1, True, False), (1, 48, 48, 1, 3, 1, True, True),
+]
+
+
+@pytest.mark.parametrize("case", RES_CASES, ids=[str(c) for c in RES_CASES])
+@pytest.mark.parametrize("variant", [0, 8], ids=["v2", "v1"])
+def test_conv1d_residual_epilogue(ops, case, variant):
+    """dst = (conv + bias + res) * scale + accum - the AMPBlock1 residual (bigvgan.py:132-141) and the resblock
+    mean (:369-375) as the generator issues them; both kernel generations against the fp64 oracle."""
+    B, Cin, Cout, T, k, d, with_acc, out_bf16 = case
+    g = torch.Generator().manual_seed(sum(int(v) for v in case))
+    x = bf(torch.randn(B, Cin, T, generator=g))
+    w = bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(B, Cout, T, generator=g)
+    acc = torch.randn(B, Cout, T, generator=g) if with_acc else torch.empty(0)
+    scale = 1.0 / 3.0
+    ref = (O.conv1d(x.double(), w.double(), b.double(), d) + res.double()) * float(torch.tensor(scale, dtype=torch.float32))
+    if with_acc:
+        ref = ref + acc.double()
+    y = ops.conv1d_res(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), acc.to(DEV), scale, out_bf16, d, "bf16",
+                       variant).cpu().double()
+    tol = (2.0 ** -8 if out_bf16 else 1e-5) * float(ref.abs().max())
+    assert (y - ref).abs().max() <= tol
+    if out_bf16:   # every value is a bf16 number
+        assert torch.equal(y.float(), bf(y.float()))
+
+
+@pytest.mark.parametrize("variant", [0, 8], ids=["v2", "v1"])
+def test_conv1d_residual_in_place_and_batch_edges(ops, variant):
+    """rows of one utterance never leak into the next one (per-utterance zero padding, clipped stores)."""
+    g = torch.Generator().manual_seed(7)
+    B, C, T, k, d = 3, 48, 300, 11, 5
+    x = bf(torch.randn(B, C, T, generator=g)); w = bf(torch.randn(C, C, k, generator=g) / (C * k) ** 0.5)
+    b = torch.randn(C, generator=g); res = torch.randn(B, C, T, generator=g)
+    y = ops.conv1d_res(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), torch.empty(0, device=DEV), 1.0, False, d, "bf16", variant)
+    for i in range(B):
+        yi = ops.conv1d_res(x[i:i + 1].contiguous().to(DEV), w.to(DEV), b.to(DEV), res[i:i + 1].contiguous().to(DEV),
+                            torch.empty(0, device=DEV), 1.0, False, d, "bf16", variant)
+        assert torch.equal(yi, y[i:i + 1])
+
+
 def test_conv_errors(ops):
     x = torch.zeros(1, 4, 8, device=DEV)
     with pytest.raises(RuntimeError):

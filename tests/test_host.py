@@ -111,7 +111,7 @@ def test_gloo_world2_sharding_and_timing_reduce(tmp_path):
         "assert torch.equal(torch.cat(got).view(-1), torch.arange(16 * w).float() * 6)\n"
         "m = shard.max_over_ranks(10.0 + r)\n"
         "assert m == 10.0 + (w - 1)\n"
-        "dist.barrier(); print('ok', r)\n" % ROOT)
+        "dist.barrier(); sys.stdout.write('ok' + str(r) + chr(10)); sys.stdout.flush()\n" % ROOT)
     import socket
     with socket.socket() as sk:          # a free port: fixed ports collide when suites run back to back
         sk.bind(("127.0.0.1", 0))
@@ -121,7 +121,7 @@ def test_gloo_world2_sharding_and_timing_reduce(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
-    assert "ok 0" in out.stdout and "ok 1" in out.stdout
+    assert "ok0" in out.stdout and "ok1" in out.stdout   # one write() per rank: no interleaving
 
 
 def test_bench_reference_arm_prints_contract_json():

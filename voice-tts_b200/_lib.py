@@ -31,6 +31,7 @@ _lib = None
 
 # name -> (restype, argtypes); every symbol include/bvg_b200.h declares
 _vp, _i, _i64, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_float)
+_f = ctypes.c_float
 SYMBOLS = {
     "bvg_abi_version": (_i, []),
     "bvg_last_error": (ctypes.c_char_p, []),
@@ -38,6 +39,7 @@ SYMBOLS = {
     "bvg_act1d_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i64, _i, _i, _vp]),
     "bvg_act1d_cl_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i64, _i, _i, _i, _i, _vp]),
     "bvg_conv1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
+    "bvg_conv1d_res_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_convtr1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_create": (_i, [ctypes.POINTER(BvgConfig), ctypes.POINTER(_vp)]),
     "bvg_destroy": (None, [_vp]),

@@ -113,7 +113,8 @@ int bvg_act1d_cl_fwd(void* dst, const void* src, const float* alpha_log, const f
 // around the channels-last kernels (test/single-layer use; the vocoder handle
 // keeps everything packed and channels-last).
 static int dense_layer(float* dst, const float* src, const float* weight, const float* bias, int B, int Cin, int Cout,
-                       int64_t T, int k, int dil, int up, int mode, cudaStream_t st) {
+                       int64_t T, int k, int dil, int up, int mode, cudaStream_t st, const float* res = nullptr,
+                       const float* accum = nullptr, float scale = 1.f, int out_bf16 = 0) {
   if (B < 0 || Cin <= 0 || Cout <= 0 || T < 0 || k <= 0) BVG_FAIL(BVG_EINVAL, "dense layer: bad dimension");
   const int variant = (mode >> 8) & 0xff;  // debug variants ride in the upper bits of `mode`
   mode &= 0xff;
@@ -132,17 +133,22 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
   const int Cout_r = round_up(Cout_n, 128);
   const int64_t Tout = up > 0 ? T * up : T;
   void *xin = nullptr, *wp = nullptr;
-  float *bp = nullptr, *yout = nullptr;
+  float *bp = nullptr, *yout = nullptr, *resp = nullptr, *accp = nullptr;
+  if ((res || accum || out_bf16) && up > 0) BVG_FAIL(BVG_EINVAL, "fused residual form is defined for conv1d only");
   const size_t b_in = (size_t)B * T * Cin_p * es, b_w = (size_t)kk * Cout_r * Cin_p * es, b_b = (size_t)Cout_r * 4,
                b_out = (size_t)B * T * Cout_n * 4;
   unsigned char* blk = nullptr;
   const size_t a = 1024;
   auto up_a = [&](size_t v) { return (v + a - 1) / a * a; };
-  BVG_CUDA(cudaMallocAsync((void**)&blk, up_a(b_in) + up_a(b_w) + up_a(b_b) + up_a(b_out), st));
+  BVG_CUDA(cudaMallocAsync((void**)&blk, up_a(b_in) + up_a(b_w) + up_a(b_b) + 3 * up_a(b_out), st));
   xin = blk; wp = blk + up_a(b_in); bp = (float*)(blk + up_a(b_in) + up_a(b_w));
   yout = (float*)(blk + up_a(b_in) + up_a(b_w) + up_a(b_b));
+  resp = (float*)((unsigned char*)yout + up_a(b_out));
+  accp = (float*)((unsigned char*)resp + up_a(b_out));
   do {
     if ((rc = bct_to_btc(xin, dt, src, B, Cin, Cin_p, T, st))) break;
+    if (res && (rc = bct_to_btc(resp, BVG_F32, res, B, Cout, Cout_p, T, st))) break;
+    if (accum && (rc = bct_to_btc(accp, BVG_F32, accum, B, Cout, Cout_p, T, st))) break;
     cudaError_t e = cudaMemsetAsync(bp, 0, b_b, st);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; break; }
     if (up > 0) {
@@ -156,15 +162,16 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
     }
     if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; break; }
     ConvArgs ca;
-    ca.in = xin; ca.w = wp; ca.bias = bp; ca.out = yout; ca.res = nullptr; ca.accum = nullptr; ca.scale = 1.f;
-    ca.in_dtype = dt; ca.w_dtype = dt; ca.out_dtype = BVG_F32;
+    ca.in = xin; ca.w = wp; ca.bias = bp; ca.out = yout; ca.res = res ? resp : nullptr;
+    ca.accum = accum ? accp : nullptr; ca.scale = scale;
+    ca.in_dtype = dt; ca.w_dtype = dt; ca.out_dtype = out_bf16 ? BVG_BF16 : BVG_F32;
     ca.B = B; ca.T = T; ca.Cin_p = Cin_p; ca.Cout_n = Cout_n; ca.Cout_r = Cout_r; ca.out_ld = Cout_n;
     ca.k = kk; ca.dil = up > 0 ? 1 : dil;
     if (dt == BVG_BF16 && conv_umma_supported(ca)) rc = conv_umma_launch(ca, variant, st);
     else rc = conv_simt_launch(ca, st);
     if (rc) break;
     // [B, T, u*Cout_p] is [B, u*T, Cout_p]
-    rc = btc_to_bct(dst, yout, BVG_F32, B, Cout, Cout_p, Tout, st);
+    rc = btc_to_bct(dst, yout, out_bf16 ? BVG_BF16 : BVG_F32, B, Cout, Cout_p, Tout, st);
   } while (0);
   cudaFreeAsync(blk, st);
   return rc;
@@ -175,6 +182,16 @@ int bvg_conv1d_fwd(float* dst, const float* src, const float* weight, const floa
   const int m = mode & 0xff;
   if (m != BVG_MODE_FP32 && m != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_conv1d_fwd: unknown mode %d", mode);
   return dense_layer(dst, src, weight, bias, B, Cin, Cout, T, k, dilation, 0, mode, (cudaStream_t)stream);
+}
+
+int bvg_conv1d_res_fwd(float* dst, const float* src, const float* weight, const float* bias, const float* res,
+                       const float* accum, float scale, int out_bf16, int B, int Cin, int Cout, int64_t T, int k,
+                       int dilation, int mode, bvg_stream_t stream) {
+  const int m = mode & 0xff;
+  if (m != BVG_MODE_FP32 && m != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_conv1d_res_fwd: unknown mode %d", mode);
+  if (out_bf16 && m != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_conv1d_res_fwd: bf16 rounding of the result needs BVG_MODE_BF16");
+  return dense_layer(dst, src, weight, bias, B, Cin, Cout, T, k, dilation, 0, mode, (cudaStream_t)stream, res, accum,
+                     scale, out_bf16);
 }
 
 int bvg_convtr1d_fwd(float* dst, const float* src, const float* weight, const float* bias, int B, int Cin, int Cout,

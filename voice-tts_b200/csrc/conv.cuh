@@ -37,6 +37,7 @@ int act1d_bct_launch(void* dst, const void* src, const float* alpha_log, const f
 
 int bct_to_btc(void* dst, int out_dtype, const float* src, int B, int C, int Cp, int64_t T, cudaStream_t st);
 int btc_to_bct(float* dst, const void* src, int in_dtype, int B, int C, int Cp, int64_t T, cudaStream_t st);
+int weight_replica_rows(int Cout_n, int Cout_r);
 int pack_conv_weight(void* wp, int dtype, const float* w, int Cout, int Cin, int k, int Cout_r, int Cin_p,
                      cudaStream_t st);
 int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int Cout_p, int Cout_r,

@@ -369,6 +369,29 @@ int make_map_4d_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, ui
   return BVG_OK;
 }
 
+// general 3-D map: element size `es` (2 = bf16, 4 = fp32), swizzle span in bytes (0 = none, 32/64/128)
+int make_map_any(CUtensorMap* m, const void* base, int es, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
+                 uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) BVG_FAIL(BVG_ENODEV, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {ld_elems * (uint64_t)es, ld_elems * d1 * (uint64_t)es};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(m, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    BVG_FAIL(BVG_ECUDA, "cuTensorMapEncodeTiled failed (%d) es=%d dims=(%llu,%llu,%llu) ld=%llu box=(%u,%u,%u) sw=%d",
+             (int)r, es, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)ld_elems, b0, b1, b2, swizzle_bytes);
+  return BVG_OK;
+}
+
 int umma_sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -391,6 +414,7 @@ bool conv_umma_supported(const ConvArgs& a) {
 int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   if (a.B <= 0 || a.T <= 0) return BVG_OK;
   if (!conv_umma_supported(a)) BVG_FAIL(BVG_EINVAL, "conv_umma: unsupported layer shape/dtype");
+  if (!(variant & 8) && conv_umma2_supported(a)) return conv_umma2_launch(a, variant, st);   // v2 kernel (default)
   if (a.Cout_n <= 128 && !(variant & 4) && conv_umma_t_fits(a)) return conv_umma_t_launch(a, variant, st);   // time-major variant
   UmmaParams p;
   p.bias = a.bias; p.out = a.out; p.res = a.res; p.accum = a.accum; p.scale = a.scale;

@@ -83,11 +83,12 @@ int btc_to_bct(float* dst, const void* src, int in_dtype, int B, int C, int Cp, 
 // Conv1d weight [Cout, Cin, k] (torch) -> Wp[k][Cout_r][Cin_p]
 template <typename Tout>
 __global__ void pack_conv_kernel(Tout* __restrict__ wp, const float* __restrict__ w, int Cout, int Cin, int k,
-                                 int Cout_r, int Cin_p) {
+                                 int Cout_r, int Cin_p, int rep_lr) {
   const int64_t n = (int64_t)k * Cout_r * Cin_p;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin_p);
-    const int co = (int)((i / Cin_p) % Cout_r);
+    int co = (int)((i / Cin_p) % Cout_r);
+    if (rep_lr) co %= rep_lr;   // narrow layers: the pad rows of the 128-row tile hold replicas (see weight_replica_rows)
     const int j = (int)(i / ((int64_t)Cin_p * Cout_r));
     float v = 0.f;
     if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin + ci) * k + j];
@@ -103,12 +104,13 @@ __global__ void pack_conv_kernel(Tout* __restrict__ wp, const float* __restrict_
 // (polyphase form of torch ConvTranspose1d)
 template <typename Tout>
 __global__ void pack_convtr_kernel(Tout* __restrict__ wp, const float* __restrict__ w, int Cin, int Cout, int u,
-                                   int Cout_p, int Cout_r, int Cin_p) {
+                                   int Cout_p, int Cout_r, int Cin_p, int rep_lr) {
   const int k = 2 * u;
   const int64_t n = (int64_t)3 * Cout_r * Cin_p;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin_p);
-    const int vc = (int)((i / Cin_p) % Cout_r);  // virtual output channel r*Cout_p + co
+    int vc = (int)((i / Cin_p) % Cout_r);  // virtual output channel r*Cout_p + co
+    if (rep_lr) vc %= rep_lr;
     const int tap = (int)(i / ((int64_t)Cin_p * Cout_r));
     float v = 0.f;
     const int r = vc / Cout_p, co = vc % Cout_p;
@@ -128,26 +130,37 @@ __global__ void pack_convtr_kernel(Tout* __restrict__ wp, const float* __restric
   }
 }
 
+// Layers whose whole output (Cout_n channels per row) fits 64 (32) MMA rows keep 2 (4) copies of
+// their weight rows in the 128-row tile: the tcgen05 kernel then finds the same result in every
+// TMEM lane group and all epilogue warps share the time columns (conv_umma2.cu).  Returns the
+// replica period in rows (0 = no replication).
+int weight_replica_rows(int Cout_n, int Cout_r) {
+  if (Cout_r != 128 || Cout_n > 64) return 0;
+  return Cout_n <= 32 ? 32 : 64;
+}
+
 int pack_conv_weight(void* wp, int dtype, const float* w, int Cout, int Cin, int k, int Cout_r, int Cin_p,
                      cudaStream_t st) {
+  const int rep_lr = weight_replica_rows(Cout < 16 ? 16 : round_up(Cout, 16), Cout_r);
   const int64_t n = (int64_t)k * Cout_r * Cin_p;
   const int blocks = (int)(ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096);
   if (dtype == BVG_BF16)
-    pack_conv_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)wp, w, Cout, Cin, k, Cout_r, Cin_p);
+    pack_conv_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)wp, w, Cout, Cin, k, Cout_r, Cin_p, rep_lr);
   else
-    pack_conv_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cout, Cin, k, Cout_r, Cin_p);
+    pack_conv_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cout, Cin, k, Cout_r, Cin_p, rep_lr);
   BVG_LAUNCHED();
   return BVG_OK;
 }
 int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int Cout_p, int Cout_r,
                        int Cin_p, cudaStream_t st) {
+  const int rep_lr = weight_replica_rows(u * Cout_p, Cout_r);
   const int64_t n = (int64_t)3 * Cout_r * Cin_p;
   const int blocks = (int)(ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096);
   if (dtype == BVG_BF16)
     pack_convtr_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)wp, w, Cin, Cout, u, Cout_p, Cout_r,
-                                                              Cin_p);
+                                                              Cin_p, rep_lr);
   else
-    pack_convtr_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cin, Cout, u, Cout_p, Cout_r, Cin_p);
+    pack_convtr_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cin, Cout, u, Cout_p, Cout_r, Cin_p, rep_lr);
   BVG_LAUNCHED();
   return BVG_OK;
 }

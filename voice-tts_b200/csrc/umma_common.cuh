@@ -24,7 +24,12 @@ int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
                 int row_bytes);
 int make_map_4d_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
                   uint32_t b2, int row_bytes);
+int make_map_any(CUtensorMap* m, const void* base, int es, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
+                 uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
 int umma_sm_count();
+// v2 channel-major kernel (conv_umma2.cu): 128-byte operand rows, TMA-store epilogue
+bool conv_umma2_supported(const ConvArgs& a);
+int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st);
 int conv_umma_t_launch(const ConvArgs& a, int variant, cudaStream_t st);
 bool conv_umma_t_fits(const ConvArgs& a);
 

@@ -113,6 +113,43 @@ def _(x, weight, bias, dilation, precision, variant):
     return x.new_empty(x.shape[0], weight.shape[0], x.shape[2])
 
 
+@torch.library.custom_op("bvg_b200::conv1d_res", mutates_args=())
+def conv1d_res(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, res: torch.Tensor, accum: torch.Tensor,
+               scale: float, out_bf16: bool, dilation: int, precision: str, variant: int) -> torch.Tensor:
+    """(conv1d(x) + bias + res) * scale + accum; empty tensors stand for absent operands
+    (AMPBlock1 residual bigvgan.py:132-141 and resblock mean :369-375 folded into the conv epilogue)."""
+    _require_cuda(x, "x")
+    B, Cin, T = x.shape
+    Cout, Cin2, k = weight.shape
+    if Cin2 != Cin or x.dtype != torch.float32:
+        raise RuntimeError("conv1d_res: expects fp32 [B,Cin,T] and weight [Cout,Cin,k]")
+    w = weight.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    keep = []
+
+    def ptr(t, shape):
+        if not t.numel():
+            return 0
+        if tuple(t.shape) != shape:
+            raise RuntimeError("conv1d_res: operand shape %s, expected %s" % (tuple(t.shape), shape))
+        tt = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        keep.append(tt)
+        return tt.data_ptr()
+
+    bptr, rptr, aptr = ptr(bias, (Cout,)), ptr(res, (B, Cout, T)), ptr(accum, (B, Cout, T))
+    y = torch.empty(B, Cout, T, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bvg_conv1d_res_fwd(y.data_ptr(), x.data_ptr(), w.data_ptr(), bptr, rptr, aptr, float(scale),
+                                            int(out_bf16), B, Cin, Cout, T, k, dilation, _mode(precision, variant),
+                                            _stream(x))
+    _lib.check(rc, "bvg_conv1d_res_fwd")
+    return y
+
+
+@conv1d_res.register_fake
+def _(x, weight, bias, res, accum, scale, out_bf16, dilation, precision, variant):
+    return x.new_empty(x.shape[0], weight.shape[0], x.shape[2])
+
+
 @torch.library.custom_op("bvg_b200::conv_transpose1d", mutates_args=())
 def conv_transpose1d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, precision: str,
                      variant: int) -> torch.Tensor:
