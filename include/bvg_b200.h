@@ -109,6 +109,14 @@ int bvg_convtr1d_fwd(float* dst, const float* src, const float* weight, const fl
 int bvg_conv1d_res_fwd(float* dst, const float* src, const float* weight, const float* bias, const float* res,
                        const float* accum, float scale, int out_bf16, int B, int Cin, int Cout, int64_t T, int k,
                        int dilation, int mode, bvg_stream_t stream);
+/* Conv1d followed by the anti-aliased activation, as `xt = c1(xt); xt = a2(xt)` in AMPBlock1.forward
+ * (bigvgan.py:136-138): dst = Activation1d_{alpha,beta}(conv1d(src) + bias).  alpha_log / beta_log: [Cout] fp32
+ * log-scale device arrays; up_taps / down_taps: 12 host floats each (as bvg_act1d_fwd).  BVG_MODE_BF16 runs ONE
+ * tcgen05 kernel (the fp32 accumulator goes through the activation in registers, the result is rounded to bf16);
+ * BVG_MODE_FP32 runs the fp32 conv and the fp32 activation kernel back to back. */
+int bvg_conv1d_act_fwd(float* dst, const float* src, const float* weight, const float* bias, const float* alpha_log,
+                       const float* beta_log, const float* up_taps, const float* down_taps, int B, int Cin, int Cout,
+                       int64_t T, int k, int dilation, int mode, bvg_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Whole generator.  Build: bvg_create -> bvg_set_tensor for every state-dict

@@ -132,3 +132,64 @@ def test_conv_errors(ops):
         ops.conv1d(x, torch.zeros(4, 4, 3, device=DEV), torch.zeros(4, device=DEV), 1, "fp16", 0)
     with pytest.raises(RuntimeError):
         ops.conv_transpose1d(x, torch.zeros(4, 2, 6, device=DEV), torch.zeros(2, device=DEV), 2, "fp32", 0)  # k != 2u
+
+
+ACT_CASES = [  # B, Cin, Cout, T, k, dil   (T chosen around the 240-output tiles / 30-row rounds of the fused kernel)
+    (1, 24, 24, 700, 3, 1), (2, 24, 24, 1500, 11, 5), (1, 48, 48, 900, 7, 3), (2, 96, 96, 300, 3, 5),
+    (1, 192, 192, 530, 7, 1), (1, 384, 384, 300, 3, 3), (1, 32, 80, 257, 3, 1), (3, 16, 16, 33, 3, 1),
+    (1, 48, 48, 1, 3, 1), (2, 64, 64, 2, 7, 1), (1, 128, 128, 5, 3, 1), (1, 40, 40, 6, 3, 1), (1, 24, 24, 7, 11, 1),
+    (1, 24, 24, 239, 3, 1), (1, 24, 24, 240, 3, 1), (1, 24, 24, 241, 3, 1), (1, 96, 96, 245, 7, 5), (2, 48, 48, 480, 11, 3),
+    (1, 768, 768, 250, 3, 1), (1, 56, 56, 31, 3, 1), (1, 24, 24, 29, 3, 1), (1, 104, 104, 123, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", ACT_CASES, ids=[str(c) for c in ACT_CASES])
+def test_conv1d_fused_activation(ops, case):
+    """Activation1d(conv1d(x) + bias) as ONE tcgen05 kernel (bigvgan.py:136-138) against the fp64 oracle composition;
+    the fp32 accumulator goes straight through the activation, only the result is rounded to bf16."""
+    B, Cin, Cout, T, k, d = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = bf(torch.randn(B, Cin, T, generator=g))
+    w = bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    al = torch.randn(Cout, generator=g) * 0.5
+    be = torch.randn(Cout, generator=g) * 0.5
+    taps = O.kaiser_taps()
+    conv = O.conv1d(x.double(), w.double(), b.double(), d)
+    ref = O.activation1d(conv, al.double(), be.double(), taps.double(), taps.double())
+    tl = taps.tolist()
+    y = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "bf16", 0).cpu().double()
+    assert y.shape == ref.shape
+    # bf16 rounding of the result (2^-9 relative) + the fast-cosine snake (~1e-6 of the argument)
+    tol = 2.0 ** -8 * float(ref.abs().max())
+    err = (y - ref).abs()
+    assert err.max() <= tol, "max err %.3e at %s (tol %.3e)" % (err.max(), (err == err.max()).nonzero()[0].tolist(), tol)
+    assert torch.equal(y.float(), bf(y.float()))
+    # the two-kernel composition (conv -> bf16 -> activation kernel) agrees to within its extra rounding step
+    y2 = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "bf16", 16).cpu().double()
+    assert (y2 - ref).abs().max() <= 2.0 ** -6 * float(ref.abs().max())
+    assert O.snr_db(ref.float(), y.float()) >= O.snr_db(ref.float(), y2.float()) - 0.5
+
+
+def test_conv1d_fused_activation_fp32_mode(ops):
+    """fp32 mode composes the fp32 conv and the fp32 activation kernel (<= 1e-5 relative)."""
+    g = torch.Generator().manual_seed(5)
+    B, C, T, k, d = 2, 24, 300, 7, 3
+    x = torch.randn(B, C, T, generator=g); w = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b = torch.randn(C, generator=g); al = torch.randn(C, generator=g) * 0.5; be = torch.randn(C, generator=g) * 0.5
+    taps = O.kaiser_taps(); tl = taps.tolist()
+    ref = O.activation1d(O.conv1d(x.double(), w.double(), b.double(), d), al.double(), be.double(), taps.double(), taps.double())
+    y = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "fp32", 0).cpu().double()
+    assert (y - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+
+
+def test_conv1d_fused_activation_batch_independence(ops):
+    g = torch.Generator().manual_seed(9)
+    B, C, T, k, d = 3, 48, 500, 11, 5
+    x = bf(torch.randn(B, C, T, generator=g)); w = bf(torch.randn(C, C, k, generator=g) / (C * k) ** 0.5)
+    b = torch.randn(C, generator=g); al = torch.randn(C, generator=g) * 0.5; be = torch.randn(C, generator=g) * 0.5
+    tl = O.kaiser_taps().tolist()
+    y = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "bf16", 0)
+    for i in range(B):
+        yi = ops.conv1d_act(x[i:i + 1].contiguous().to(DEV), w.to(DEV), b.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "bf16", 0)
+        assert torch.equal(yi, y[i:i + 1])

@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbvg_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("BVG_LIB_NAME", "libbvg_b200.so"))   # BVG_LIB_NAME: debug builds only
 
 F32, BF16 = 0, 1
 MODE_FP32, MODE_BF16 = 0, 1
@@ -40,6 +40,7 @@ SYMBOLS = {
     "bvg_act1d_cl_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i64, _i, _i, _i, _i, _vp]),
     "bvg_conv1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_conv1d_res_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i64, _i, _i, _i, _vp]),
+    "bvg_conv1d_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_convtr1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_create": (_i, [ctypes.POINTER(BvgConfig), ctypes.POINTER(_vp)]),
     "bvg_destroy": (None, [_vp]),

@@ -6,8 +6,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libbvg_b200.so")
-SOURCES = ["api.cu", "act1d_cl.cu", "act1d_bct.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_t.cu", "conv_umma2.cu", "vocoder.cu"]
+LIB = os.path.join(HERE, os.environ.get("BVG_LIB_NAME", "libbvg_b200.so"))   # BVG_LIB_NAME / BVG_EXTRA_FLAGS: debug builds
+SOURCES = ["api.cu", "act1d_cl.cu", "act1d_bct.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_t.cu", "conv_umma2.cu", "conv_umma2a.cu", "vocoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
@@ -31,12 +31,12 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", os.path.basename(LIB))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("BVG_EXTRA_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:

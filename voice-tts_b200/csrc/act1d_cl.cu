@@ -23,13 +23,13 @@ template <typename T, int VEC>
 struct VecIO;
 template <>
 struct VecIO<float, 1> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = BVG_LDG(p); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
 };
 template <>
 struct VecIO<float, 2> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[2]) {
-    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    float2 t = BVG_LDG(reinterpret_cast<const float2*>(p));
     v[0] = t.x;
     v[1] = t.y;
   }
@@ -40,7 +40,7 @@ struct VecIO<float, 2> {
 template <>
 struct VecIO<__nv_bfloat16, 1> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) {
-    v[0] = __bfloat162float(*p);
+    v[0] = ld_mut_f32<__nv_bfloat16>(p);
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) {
     *p = __float2bfloat16_rn(v[0]);
@@ -49,7 +49,7 @@ struct VecIO<__nv_bfloat16, 1> {
 template <>
 struct VecIO<__nv_bfloat16, 2> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[2]) {
-    uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(p));
+    uint32_t raw = BVG_LDG(reinterpret_cast<const uint32_t*>(p));
     v[0] = __uint_as_float(raw << 16);
     v[1] = __uint_as_float(raw & 0xffff0000u);
   }
@@ -221,7 +221,7 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
 template <typename T> struct PairIO;
 template <> struct PairIO<float> {
   typedef float2 raw_t;
-  static __device__ __forceinline__ raw_t ldraw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ raw_t ldraw(const float* p) { return BVG_LDG(reinterpret_cast<const float2*>(p)); }
   static __device__ __forceinline__ f32x2 cvt(raw_t r) { return pk2(r.x, r.y); }
   static __device__ __forceinline__ void store(float* p, f32x2 v) {
     float a, b; upk2(v, a, b);
@@ -230,7 +230,7 @@ template <> struct PairIO<float> {
 };
 template <> struct PairIO<__nv_bfloat16> {
   typedef uint32_t raw_t;
-  static __device__ __forceinline__ raw_t ldraw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ raw_t ldraw(const __nv_bfloat16* p) { return BVG_LDG(reinterpret_cast<const uint32_t*>(p)); }
   static __device__ __forceinline__ f32x2 cvt(raw_t r) { return pk2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, f32x2 v) {
     float a, b; upk2(v, a, b);
@@ -259,8 +259,11 @@ template <> struct PairIO<__nv_bfloat16> {
 
 // interior segments only (t0 >= 5, t0 + L + 4 <= T - 1, L = 6n-5); edge segments are
 // handled by the scalar kernel's generic path in a second (tiny) launch.
+// 256-thread blocks: one block (8 warps, <= 96 registers) fits on an SM next to a persistent
+// tcgen05 conv CTA of another AMP block (vocoder.cu: blocks of a stage run on separate streams).
+constexpr int kPackedThreads = 128;
 template <typename Tin, typename Tout, bool FAST>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kPackedThreads)
 act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
                        const float* __restrict__ beta_log, const TapsPacked tp, int B, int64_t T, int C, int L,
                        int nseg_int, int head_len, int64_t nitems) {
@@ -352,9 +355,9 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
     TapsPacked tp;
     make_taps_packed(&tp, taps);
     const int64_t nitems = (int64_t)B * n_int * P;
-    const int64_t blocks = ceil_div(nitems, threads);
+    const int64_t blocks = ceil_div(nitems, kPackedThreads);
     if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
-    act1d_cl_packed_kernel<Tin, Tout, FAST><<<(unsigned)blocks, threads, 0, st>>>(
+    act1d_cl_packed_kernel<Tin, Tout, FAST><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
         (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, L, (int)n_int, kEdge, nitems);
     BVG_LAUNCHED();
   }

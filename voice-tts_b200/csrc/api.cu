@@ -114,7 +114,8 @@ int bvg_act1d_cl_fwd(void* dst, const void* src, const float* alpha_log, const f
 // keeps everything packed and channels-last).
 static int dense_layer(float* dst, const float* src, const float* weight, const float* bias, int B, int Cin, int Cout,
                        int64_t T, int k, int dil, int up, int mode, cudaStream_t st, const float* res = nullptr,
-                       const float* accum = nullptr, float scale = 1.f, int out_bf16 = 0) {
+                       const float* accum = nullptr, float scale = 1.f, int out_bf16 = 0,
+                       const float* act_alpha = nullptr, const float* act_beta = nullptr, const Taps* act_taps = nullptr) {
   if (B < 0 || Cin <= 0 || Cout <= 0 || T < 0 || k <= 0) BVG_FAIL(BVG_EINVAL, "dense layer: bad dimension");
   const int variant = (mode >> 8) & 0xff;  // debug variants ride in the upper bits of `mode`
   mode &= 0xff;
@@ -134,18 +135,27 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
   const int64_t Tout = up > 0 ? T * up : T;
   void *xin = nullptr, *wp = nullptr;
   float *bp = nullptr, *yout = nullptr, *resp = nullptr, *accp = nullptr;
-  if ((res || accum || out_bf16) && up > 0) BVG_FAIL(BVG_EINVAL, "fused residual form is defined for conv1d only");
+  if ((res || accum || out_bf16 || act_taps) && up > 0) BVG_FAIL(BVG_EINVAL, "fused residual / activation forms are defined for conv1d only");
+  if (act_taps && (res || accum)) BVG_FAIL(BVG_EINVAL, "fused activation form takes no residual");
   const size_t b_in = (size_t)B * T * Cin_p * es, b_w = (size_t)kk * Cout_r * Cin_p * es, b_b = (size_t)Cout_r * 4,
                b_out = (size_t)B * T * Cout_n * 4;
   unsigned char* blk = nullptr;
   const size_t a = 1024;
   auto up_a = [&](size_t v) { return (v + a - 1) / a * a; };
-  BVG_CUDA(cudaMallocAsync((void**)&blk, up_a(b_in) + up_a(b_w) + up_a(b_b) + 3 * up_a(b_out), st));
+  BVG_CUDA(cudaMallocAsync((void**)&blk, up_a(b_in) + up_a(b_w) + 3 * up_a(b_b) + 3 * up_a(b_out), st));
   xin = blk; wp = blk + up_a(b_in); bp = (float*)(blk + up_a(b_in) + up_a(b_w));
   yout = (float*)(blk + up_a(b_in) + up_a(b_w) + up_a(b_b));
   resp = (float*)((unsigned char*)yout + up_a(b_out));
   accp = (float*)((unsigned char*)resp + up_a(b_out));
+  float* alp = (float*)((unsigned char*)accp + up_a(b_out));   // zero-padded alpha / beta of the fused activation
+  float* bep = (float*)((unsigned char*)alp + up_a(b_b));
   do {
+    if (act_taps) {
+      cudaError_t ea = cudaMemsetAsync(alp, 0, 2 * up_a(b_b), st);
+      if (ea == cudaSuccess) ea = cudaMemcpyAsync(alp, act_alpha, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      if (ea == cudaSuccess) ea = cudaMemcpyAsync(bep, act_beta, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      if (ea != cudaSuccess) { set_error("activation parameters: %s", cudaGetErrorString(ea)); rc = BVG_ECUDA; break; }
+    }
     if ((rc = bct_to_btc(xin, dt, src, B, Cin, Cin_p, T, st))) break;
     if (res && (rc = bct_to_btc(resp, BVG_F32, res, B, Cout, Cout_p, T, st))) break;
     if (accum && (rc = bct_to_btc(accp, BVG_F32, accum, B, Cout, Cout_p, T, st))) break;
@@ -167,6 +177,24 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
     ca.in_dtype = dt; ca.w_dtype = dt; ca.out_dtype = out_bf16 ? BVG_BF16 : BVG_F32;
     ca.B = B; ca.T = T; ca.Cin_p = Cin_p; ca.Cout_n = Cout_n; ca.Cout_r = Cout_r; ca.out_ld = Cout_n;
     ca.k = kk; ca.dil = up > 0 ? 1 : dil;
+    if (act_taps) {
+      // conv + bias, then Activation1d: one kernel in bf16 mode (result rounded to bf16), two kernels otherwise
+      ca.out_dtype = dt;
+      if (dt == BVG_BF16 && !(variant & 16) && conv_act_fused_supported(ca)) {
+        rc = conv_act_fused_launch(ca, alp, bep, *act_taps, st);
+        if (rc) break;
+        rc = btc_to_bct(dst, yout, BVG_BF16, B, Cout, Cout_p, Tout, st);
+        break;
+      }
+      ca.out = resp;   // intermediate conv result (operand dtype)
+      if (dt == BVG_BF16 && conv_umma_supported(ca)) rc = conv_umma_launch(ca, variant, st);
+      else rc = conv_simt_launch(ca, st);
+      if (rc) break;
+      rc = act1d_cl_launch(yout, resp, alp, bep, *act_taps, B, T, Cout_n, dt, dt, dt == BVG_BF16, st);
+      if (rc) break;
+      rc = btc_to_bct(dst, yout, dt, B, Cout, Cout_p, Tout, st);
+      break;
+    }
     if (dt == BVG_BF16 && conv_umma_supported(ca)) rc = conv_umma_launch(ca, variant, st);
     else rc = conv_simt_launch(ca, st);
     if (rc) break;
@@ -192,6 +220,18 @@ int bvg_conv1d_res_fwd(float* dst, const float* src, const float* weight, const 
   if (out_bf16 && m != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_conv1d_res_fwd: bf16 rounding of the result needs BVG_MODE_BF16");
   return dense_layer(dst, src, weight, bias, B, Cin, Cout, T, k, dilation, 0, mode, (cudaStream_t)stream, res, accum,
                      scale, out_bf16);
+}
+
+int bvg_conv1d_act_fwd(float* dst, const float* src, const float* weight, const float* bias, const float* alpha_log,
+                       const float* beta_log, const float* up_taps, const float* down_taps, int B, int Cin, int Cout,
+                       int64_t T, int k, int dilation, int mode, bvg_stream_t stream) {
+  const int m = mode & 0xff;
+  if (m != BVG_MODE_FP32 && m != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_conv1d_act_fwd: unknown mode %d", mode);
+  if (!alpha_log || !beta_log || !up_taps || !down_taps) BVG_FAIL(BVG_EINVAL, "bvg_conv1d_act_fwd: null activation parameter");
+  Taps taps;
+  host_taps(&taps, up_taps, down_taps);
+  return dense_layer(dst, src, weight, bias, B, Cin, Cout, T, k, dilation, 0, mode, (cudaStream_t)stream, nullptr, nullptr,
+                     1.f, 0, alpha_log, beta_log, &taps);
 }
 
 int bvg_convtr1d_fwd(float* dst, const float* src, const float* weight, const float* bias, int B, int Cin, int Cout,

@@ -10,6 +10,14 @@
 
 #include "../../include/bvg_b200.h"
 
+// Loads of tensors that other kernels rewrite (activations, residual stream) bypass L1 (ld.global.cg):
+// with the AMP blocks of a stage running on separate streams, kernels of different streams share SMs
+// back to back and L1 / non-coherent (ld.global.nc) lines left by an earlier reader of the same
+// address were observed to survive into a later kernel of another launch (measured on B200: a few
+// stale 128-byte lines per forward with __ldg, none with __ldcg).  L2 is the point of coherence.
+// Read-only parameters (weights, bias, alpha/beta, taps) keep __ldg.
+#define BVG_LDG(p) __ldcg(p)
+
 namespace bvg {
 
 // ---------------------------------------------------------------- errors ----
@@ -61,6 +69,16 @@ template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// one element of a tensor another kernel may rewrite (see BVG_LDG), as fp32
+template <typename T>
+__device__ __forceinline__ float ld_mut_f32(const T* p);
+template <>
+__device__ __forceinline__ float ld_mut_f32<float>(const float* p) { return BVG_LDG(p); }
+template <>
+__device__ __forceinline__ float ld_mut_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float((uint32_t)BVG_LDG(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
 
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
@@ -255,6 +273,28 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 4 / 2 / 1 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r0) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
+}
+// wait for this thread's TMEM loads; the registers ride through the asm so that no use of them can be
+// scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait6(uint32_t (&r)[6]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5])::"memory");
+}
+__device__ __forceinline__ void tmem_ld_wait5(uint32_t (&r)[5]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4])::"memory");
 }
 
 #endif  // __CUDACC__

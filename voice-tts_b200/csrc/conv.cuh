@@ -29,6 +29,9 @@ int conv_simt_launch(const ConvArgs& a, cudaStream_t st);
 // tcgen05 implicit-GEMM path: in/w must be bf16.  `variant` selects debug variants (0 = default).
 int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st);
 bool conv_umma_supported(const ConvArgs& a);
+// Conv1d + bias followed by Activation1d (alpha/beta log-scale per output channel), bf16 result, one kernel
+bool conv_act_fused_supported(const ConvArgs& a);
+int conv_act_fused_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps, cudaStream_t st);
 
 int act1d_cl_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,
                     int B, int64_t T, int C, int in_dtype, int out_dtype, bool fast, cudaStream_t st);

@@ -42,7 +42,7 @@ conv_simt_kernel(ConvArgs a) {
       if (trow_ok) {
         const Tin* p = in + tsrc * a.Cin_p + ci0 + lq;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xv[q] = to_f32<Tin>(p[q]);
+        for (int q = 0; q < 4; ++q) xv[q] = ld_mut_f32<Tin>(p + q);
       }
       if (wrow_ok) {
         const Tw* p = w + ((int64_t)j * a.Cout_r + wrow) * a.Cin_p + ci0 + lq;
@@ -81,9 +81,9 @@ conv_simt_kernel(ConvArgs a) {
       if (co >= a.Cout_n) continue;
       float v = acc[i][jj];
       if (a.bias) v += a.bias[co];
-      if (a.res) v += a.res[rowoff + co];
+      if (a.res) v += BVG_LDG(a.res + rowoff + co);
       v *= a.scale;
-      if (a.accum) v += a.accum[rowoff + co];
+      if (a.accum) v += BVG_LDG(a.accum + rowoff + co);
       reinterpret_cast<Tout*>(a.out)[rowoff + co] = from_f32<Tout>(v);
     }
   }

@@ -21,7 +21,7 @@ __global__ void bct_to_btc_kernel(Tout* __restrict__ dst, const Tin* __restrict_
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i;
     const int64_t t = t0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && t < T) ? to_f32<Tin>(s[(int64_t)c * T + t]) : 0.f;
+    tile[i][threadIdx.x] = (c < C && t < T) ? ld_mut_f32<Tin>(s + (int64_t)c * T + t) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -43,7 +43,7 @@ __global__ void btc_to_bct_kernel(Tout* __restrict__ dst, const Tin* __restrict_
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int64_t t = t0 + i;
     const int c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (t < T && c < Cp) ? to_f32<Tin>(s[t * Cp + c]) : 0.f;
+    tile[i][threadIdx.x] = (t < T && c < Cp) ? ld_mut_f32<Tin>(s + t * Cp + c) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -187,7 +187,7 @@ __global__ void conv_post_kernel(Tout* __restrict__ dst, const Tin* __restrict__
     for (int c = 0; c < Cp; c += 8) {
       float v[8];
       if (sizeof(Tin) == 2) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row + c));
+        const uint4 raw = BVG_LDG(reinterpret_cast<const uint4*>(row + c));
         const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -195,8 +195,8 @@ __global__ void conv_post_kernel(Tout* __restrict__ dst, const Tin* __restrict__
           v[2 * q + 1] = __uint_as_float(r[q] & 0xffff0000u);
         }
       } else {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(row + c));
-        const float4 bq = __ldg(reinterpret_cast<const float4*>(row + c) + 1);
+        const float4 a = BVG_LDG(reinterpret_cast<const float4*>(row + c));
+        const float4 bq = BVG_LDG(reinterpret_cast<const float4*>(row + c) + 1);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
         v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
       }

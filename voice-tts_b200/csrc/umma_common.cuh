@@ -30,6 +30,9 @@ int umma_sm_count();
 // v2 channel-major kernel (conv_umma2.cu): 128-byte operand rows, TMA-store epilogue
 bool conv_umma2_supported(const ConvArgs& a);
 int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st);
+// v2 kernel with the following Activation1d fused into its epilogue (conv_umma2a.cu); bf16 output only
+bool conv_umma2a_supported(const ConvArgs& a);
+int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps, cudaStream_t st);
 int conv_umma_t_launch(const ConvArgs& a, int variant, cudaStream_t st);
 bool conv_umma_t_fits(const ConvArgs& a);
 

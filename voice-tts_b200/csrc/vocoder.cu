@@ -61,6 +61,10 @@ struct bvg_vocoder {
   bool finalized = false;
   // options
   int opt_graph = 0, opt_conv_impl = 0, opt_umma_variant = 0, opt_fast_sin = -1;
+  int opt_fuse_act = 1;            // conv1 of an AMP unit applies the following activation in its epilogue (bf16 mode)
+  int opt_streams = 1;             // AMP blocks of one stage run on up to this many streams (1 = serial; >1 experimental)
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // internal streams for AMP blocks 0 .. nk-2
+  cudaEvent_t ev_fork = nullptr, ev_blk[3] = {nullptr, nullptr, nullptr};
   int64_t opt_ws_cap_mb = 24 * 1024;
   // workspace
   void* arena = nullptr;
@@ -119,10 +123,18 @@ static int alloc_act(ActW& a, int C) {
   return BVG_OK;
 }
 
+// a1 / m / a2 / y exist once per concurrently running AMP block (nb sets)
 struct Buffers {
-  void *mel, *p0, *nx, *a1, *m, *a2;
-  float *x, *y, *xs;
+  void *mel, *p0, *nx, *a1[4], *m[4], *a2[4];
+  float *x, *y[4], *xs;
+  int nb;
 };
+
+static int n_block_streams(const bvg_vocoder* v) {
+  int n = v->opt_streams < 1 ? 1 : v->opt_streams;
+  if (n > v->nk) n = v->nk;
+  return n > 4 ? 4 : n;
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -141,17 +153,25 @@ static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
   const size_t o_mel = take((size_t)B * T0 * v->mel_p * es);
   const size_t o_p0 = take((size_t)B * T0 * v->Cp[0] * es);
   const size_t o_nx = take(nmax * es);
-  const size_t o_a1 = take(nmax * es);
-  const size_t o_m = take(nmax * es);
-  const size_t o_a2 = take(nmax * es);
   const size_t o_x = take(nmax * 4);
-  const size_t o_y = take(nmax * 4);
   const size_t o_xs = take(nmax * 4);
+  const int nb = n_block_streams(v);
+  size_t o_a1[4], o_m[4], o_a2[4], o_y[4];
+  for (int j = 0; j < nb; ++j) {
+    o_a1[j] = take(nmax * es);
+    o_m[j] = take(nmax * es);
+    o_a2[j] = take(nmax * es);
+    o_y[j] = take(nmax * 4);
+  }
   if (out) {
     unsigned char* base = (unsigned char*)v->arena;
     out->mel = base + o_mel; out->p0 = base + o_p0; out->nx = base + o_nx;
-    out->a1 = base + o_a1; out->m = base + o_m; out->a2 = base + o_a2;
-    out->x = (float*)(base + o_x); out->y = (float*)(base + o_y); out->xs = (float*)(base + o_xs);
+    out->x = (float*)(base + o_x); out->xs = (float*)(base + o_xs);
+    out->nb = nb;
+    for (int j = 0; j < nb; ++j) {
+      out->a1[j] = base + o_a1[j]; out->m[j] = base + o_m[j]; out->a2[j] = base + o_a2[j];
+      out->y[j] = (float*)(base + o_y[j]);
+    }
   }
   return off;
 }
@@ -203,6 +223,32 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
   return umma ? conv_umma_launch(a, v->opt_umma_variant, st) : conv_simt_launch(a, st);
 }
 
+// c1 followed by a2 of one AMP unit (bigvgan.py:136-138) as ONE launch when the fused kernel takes the layer
+static bool can_fuse_conv_act(const bvg_vocoder* v, const ConvW& c, const void* in, void* out, int B, int64_t T) {
+  if (!v->opt_fuse_act || v->cfg.mode != BVG_MODE_BF16 || v->opt_conv_impl == 1 || v->opt_fast_sin == 0) return false;
+  // measured on B200 (profiles/r01_layer_times_*.txt): for <= 64-channel k = 3 layers the epilogue activation (two
+  // warps per scheduler, idle replica lanes) costs more than the stand-alone kernel it replaces; opt_fuse_act = 2 forces it
+  if (v->opt_fuse_act == 1 && c.Cout_n <= 64 && c.k == 3) return false;
+  ConvArgs a;
+  a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = nullptr; a.accum = nullptr; a.scale = 1.f;
+  a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
+  a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
+  a.k = c.k; a.dil = c.dil;
+  return conv_act_fused_supported(a);
+}
+static int run_conv_act(bvg_vocoder* v, const ConvW& c, const ActW& act, const void* in, void* out, int B, int64_t T,
+                        cudaStream_t st) {
+  ConvArgs a;
+  a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = nullptr; a.accum = nullptr; a.scale = 1.f;
+  a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
+  a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
+  a.k = c.k; a.dil = c.dil;
+  // accounted as a conv launch: algorithmic conv flops; the fused activation's algorithmic bytes are zero by construction
+  ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
+  ps.cin = c.Cin; ps.cout = c.Cout; ps.k = c.k_torch; ps.dil = 100 + c.dil; ps.rows = (long long)B * T;
+  return conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st);
+}
+
 static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, void* out, int out_dt, int B,
                    int64_t T, cudaStream_t st) {
   const bool fast = v->opt_fast_sin >= 0 ? v->opt_fast_sin != 0 : v->cfg.mode == BVG_MODE_BF16;
@@ -212,10 +258,63 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, a.Cp, in_dt, out_dt, fast, st);
 }
 
+// ---- debug: order-independent checksums of intermediate tensors (BVG_DBG_SUMS=1), printed per forward ----
+__global__ void dbg_sum_kernel(const uint32_t* __restrict__ p, size_t n, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t w = __ldcg(p + i);
+    acc += (unsigned long long)w * (unsigned long long)((i % 1000003u) + 1u);
+  }
+  atomicAdd(out, acc);
+}
+struct DbgSums {
+  bool on = getenv("BVG_DBG_SUMS") != nullptr;
+  unsigned long long* dev = nullptr;
+  std::vector<std::string> tags;
+  void add(const void* p, size_t bytes, const char* tag, int a, int b, int c, cudaStream_t st) {
+    if (!on) return;
+    if (!dev) { cudaMalloc((void**)&dev, 4096 * 8); }
+    if (tags.size() >= 4096) return;
+    const size_t idx = tags.size();
+    char buf[96]; snprintf(buf, sizeof(buf), "%s[%d,%d,%d]", tag, a, b, c);
+    tags.push_back(buf);
+    cudaMemsetAsync(dev + idx, 0, 8, st);
+    dbg_sum_kernel<<<296, 256, 0, st>>>((const uint32_t*)p, bytes / 4, dev + idx);
+  }
+  void flush() {
+    if (!on || tags.empty()) return;
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> h(tags.size());
+    cudaMemcpy(h.data(), dev, tags.size() * 8, cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < tags.size(); ++i) fprintf(stderr, "dbgsum %s %016llx\n", tags[i].c_str(), h[i]);
+    tags.clear();
+  }
+};
+static DbgSums g_dbg;
+
+// internal streams / events for the concurrent AMP blocks (created on first use)
+static int ensure_streams(bvg_vocoder* v) {
+  for (int i = 0; i < 3; ++i) {
+    if (!v->aux[i]) BVG_CUDA(cudaStreamCreateWithFlags(&v->aux[i], cudaStreamNonBlocking));
+    if (!v->ev_blk[i]) BVG_CUDA(cudaEventCreateWithFlags(&v->ev_blk[i], cudaEventDisableTiming));
+  }
+  if (!v->ev_fork) BVG_CUDA(cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming));
+  return BVG_OK;
+}
+
 // the layer sequence between the mel transpose and conv_post (graph-capturable)
+//
+// The nk AMP blocks of a stage read the same X and are independent up to the running sum XS
+// (bigvgan.py:369-375), so they are issued on separate streams: the FP32-pipe-bound activation
+// kernels of one block run on the SMs beside the tensor-pipe-bound persistent conv CTAs of another.
+// Block nk-1 (the longest, k = 11) stays on the caller's stream; block j's last conv waits for block
+// j-1's (XS accumulates in block order, so the result is bit-identical to the serial schedule).
 static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream_t st) {
   const int adt = v->act_dt;
-  int rc = run_conv(v, v->conv_pre, bf.mel, adt, bf.p0, adt, nullptr, nullptr, 1.f, B, T0, st);
+  const int nb = bf.nb;
+  int rc = BVG_OK;
+  if (nb > 1 && (rc = ensure_streams(v))) return rc;
+  rc = run_conv(v, v->conv_pre, bf.mel, adt, bf.p0, adt, nullptr, nullptr, 1.f, B, T0, st);
   if (rc) return rc;
   const void* stage_in = bf.p0;
   int64_t T = T0;
@@ -225,31 +324,54 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
     if (rc) return rc;
     T *= v->cfg.upsample_rates[i];
     const bool last_stage = (i == v->nst - 1);
+    if (nb > 1) BVG_CUDA(cudaEventRecord(v->ev_fork, st));
     for (int j = 0; j < v->nk; ++j) {
+      // block -> (stream, buffer set): the last block on the caller's stream, the others round-robin on aux streams
+      const int slot = nb > 1 ? (j == v->nk - 1 ? nb - 1 : j % (nb - 1)) : 0;
+      cudaStream_t sj = (nb > 1 && j != v->nk - 1) ? v->aux[slot] : st;
+      static const bool dbg_one_aux = getenv("BVG_DBG_ONE_AUX") != nullptr;   // debug: all aux blocks on aux[0], own buffers
+      if (dbg_one_aux && sj != st) sj = v->aux[0];
+      if (sj != st) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_fork, 0));
+      static const int dbg_serial = getenv("BVG_SERIAL_BLOCKS") ? atoi(getenv("BVG_SERIAL_BLOCKS")) : 0;   // debug: bit j = block j starts after block j-1
+      if (((dbg_serial >> j) & 1) && nb > 1 && j > 0) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0));
       const float* cur = bf.x;
       for (int l = 0; l < v->nd; ++l) {
         const int ci = (i * v->nk + j) * v->nd + l;
         const int ai = (i * v->nk + j) * 2 * v->nd + 2 * l;
-        rc = run_act(v, v->acts[ai], cur, BVG_F32, bf.a1, adt, B, T, st);
+        rc = run_act(v, v->acts[ai], cur, BVG_F32, bf.a1[slot], adt, B, T, sj);
         if (rc) return rc;
-        rc = run_conv(v, v->convs1[ci], bf.a1, adt, bf.m, adt, nullptr, nullptr, 1.f, B, T, st);
-        if (rc) return rc;
-        rc = run_act(v, v->acts[ai + 1], bf.m, adt, bf.a2, adt, B, T, st);
-        if (rc) return rc;
+        const size_t nel = (size_t)B * T * v->Cp[i + 1];
+        g_dbg.add(bf.a1[slot], nel * dtype_size(adt), "a1", i, j, l, sj);
+        if (can_fuse_conv_act(v, v->convs1[ci], bf.a1[slot], bf.a2[slot], B, T)) {
+          rc = run_conv_act(v, v->convs1[ci], v->acts[ai + 1], bf.a1[slot], bf.a2[slot], B, T, sj);
+          if (rc) return rc;
+        } else {
+          rc = run_conv(v, v->convs1[ci], bf.a1[slot], adt, bf.m[slot], adt, nullptr, nullptr, 1.f, B, T, sj);
+          if (rc) return rc;
+          g_dbg.add(bf.m[slot], nel * dtype_size(adt), "m", i, j, l, sj);
+          rc = run_act(v, v->acts[ai + 1], bf.m[slot], adt, bf.a2[slot], adt, B, T, sj);
+          if (rc) return rc;
+        }
+        g_dbg.add(bf.a2[slot], nel * dtype_size(adt), "a2", i, j, l, sj);
         if (l < v->nd - 1) {
-          rc = run_conv(v, v->convs2[ci], bf.a2, adt, bf.y, BVG_F32, cur, nullptr, 1.f, B, T, st);
-          cur = bf.y;
+          rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, bf.y[slot], BVG_F32, cur, nullptr, 1.f, B, T, sj);
+          cur = bf.y[slot];
+          g_dbg.add(bf.y[slot], nel * 4, "y", i, j, l, sj);
         } else {
           const bool to_next = (j == v->nk - 1) && !last_stage;
-          rc = run_conv(v, v->convs2[ci], bf.a2, adt, to_next ? bf.nx : (void*)bf.xs, to_next ? adt : BVG_F32, cur,
-                        j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, st);
+          if (nb > 1 && j > 0) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0));   // XS of block j-1
+          rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, to_next ? bf.nx : (void*)bf.xs, to_next ? adt : BVG_F32, cur,
+                        j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, sj);
+          if (rc) return rc;
+          g_dbg.add(to_next ? bf.nx : (void*)bf.xs, nel * (to_next ? dtype_size(adt) : 4), "xs", i, j, l, sj);
+          if (nb > 1 && j < v->nk - 1) BVG_CUDA(cudaEventRecord(v->ev_blk[j % 3], sj));
         }
         if (rc) return rc;
       }
     }
     stage_in = bf.nx;
   }
-  return run_act(v, v->act_post, bf.xs, BVG_F32, bf.a1, adt, B, T, st);
+  return run_act(v, v->act_post, bf.xs, BVG_F32, bf.a1[0], adt, B, T, st);
 }
 
 static int forward_chunk(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, int B, int T0,
@@ -291,7 +413,7 @@ static int forward_chunk(bvg_vocoder* v, const float* mel, void* wav, int wav_i1
   }
   const int64_t Tw = (int64_t)T0 * v->total_up;
   ProfScope ps(v, st, CAT_OTHER, 0.0);
-  return conv_post_launch(wav, wav_i16, bf.a1, v->act_dt, v->post_w, v->post_bias, B, v->Cp[v->nst], Tw,
+  return conv_post_launch(wav, wav_i16, bf.a1[0], v->act_dt, v->post_w, v->post_bias, B, v->Cp[v->nst], Tw,
                           v->cfg.use_tanh_at_final, st);
 }
 
@@ -332,6 +454,7 @@ int vocoder_forward(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, in
     if (rc) return rc;
   }
   v->last_launches = (int)(g_launches.load() - l0);
+  g_dbg.flush();
   return BVG_OK;
 }
 
@@ -633,6 +756,8 @@ extern "C" void bvg_destroy(bvg_vocoder* v) {
   for (auto& e : v->ev_pool) cudaEventDestroy(e);
   for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
   if (v->arena) cudaFree(v->arena);
+  for (int i = 0; i < 3; ++i) { if (v->aux[i]) cudaStreamDestroy(v->aux[i]); if (v->ev_blk[i]) cudaEventDestroy(v->ev_blk[i]); }
+  if (v->ev_fork) cudaEventDestroy(v->ev_fork);
   if (v->pin_mel) cudaFreeHost(v->pin_mel);
   if (v->pin_wav) cudaFreeHost(v->pin_wav);
   if (v->dev_mel) cudaFree(v->dev_mel);
@@ -648,6 +773,24 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
   else if (!strcmp(key, "fast_sin")) v->opt_fast_sin = value;
   else if (!strcmp(key, "workspace_mb")) v->opt_ws_cap_mb = value;
   else if (!strcmp(key, "profile")) v->opt_profile = value;
+  else if (!strcmp(key, "fuse_act")) {
+    if (value != v->opt_fuse_act) {
+      BVG_CUDA(cudaSetDevice(v->cfg.device));
+      BVG_CUDA(cudaDeviceSynchronize());
+      for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
+      v->graphs.clear();
+      v->opt_fuse_act = value;
+    }
+  }
+  else if (!strcmp(key, "streams")) {
+    if (value != v->opt_streams) {   // the workspace layout (and any captured graph) depends on it
+      BVG_CUDA(cudaSetDevice(v->cfg.device));
+      BVG_CUDA(cudaDeviceSynchronize());
+      for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
+      v->graphs.clear();
+      v->opt_streams = value;
+    }
+  }
   else BVG_FAIL(BVG_EINVAL, "bvg_set_option: unknown option '%s'", key);
   return BVG_OK;
 }

@@ -150,6 +150,40 @@ def _(x, weight, bias, res, accum, scale, out_bf16, dilation, precision, variant
     return x.new_empty(x.shape[0], weight.shape[0], x.shape[2])
 
 
+@torch.library.custom_op("bvg_b200::conv1d_act", mutates_args=())
+def conv1d_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, alpha_log: torch.Tensor,
+               beta_log: torch.Tensor, up_taps: List[float], down_taps: List[float], dilation: int, precision: str,
+               variant: int) -> torch.Tensor:
+    """Activation1d(conv1d(x) + bias): `xt = c1(xt); xt = a2(xt)` of AMPBlock1.forward (bigvgan.py:136-138) as one
+    tcgen05 kernel in bf16 mode (variant 16 forces the two-kernel composition)."""
+    _require_cuda(x, "x")
+    B, Cin, T = x.shape
+    Cout, Cin2, k = weight.shape
+    if Cin2 != Cin or x.dtype != torch.float32:
+        raise RuntimeError("conv1d_act: expects fp32 [B,Cin,T] and weight [Cout,Cin,k]")
+    w = weight.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    a = alpha_log.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    b = beta_log.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    if a.numel() != Cout or b.numel() != Cout:
+        raise RuntimeError("conv1d_act: alpha/beta must have Cout=%d elements" % Cout)
+    bptr = 0
+    if bias.numel():
+        bb = bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        bptr = bb.data_ptr()
+    y = torch.empty(B, Cout, T, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bvg_conv1d_act_fwd(y.data_ptr(), x.data_ptr(), w.data_ptr(), bptr, a.data_ptr(), b.data_ptr(),
+                                            _lib.taps_array(up_taps), _lib.taps_array(down_taps), B, Cin, Cout, T, k,
+                                            dilation, _mode(precision, variant), _stream(x))
+    _lib.check(rc, "bvg_conv1d_act_fwd")
+    return y
+
+
+@conv1d_act.register_fake
+def _(x, weight, bias, alpha_log, beta_log, up_taps, down_taps, dilation, precision, variant):
+    return x.new_empty(x.shape[0], weight.shape[0], x.shape[2])
+
+
 @torch.library.custom_op("bvg_b200::conv_transpose1d", mutates_args=())
 def conv_transpose1d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, precision: str,
                      variant: int) -> torch.Tensor:
