@@ -202,12 +202,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (dbg) p.dbg[U2D_A_EMPTY0 + mine] = w0;
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer: ONE thread, and as few instructions per tap
-    // as possible - with 2 K steps per tap (<= 32 input channels) the tensor pipe needs only ~260 cycles
-    // per tap, so a long issue path (ring bookkeeping, 64-bit descriptor arithmetic, per-tap election) is
-    // what the narrow layers end up waiting for (measured: ~400 cycles per tap before this rewrite).
-    // Only the low descriptor word changes: (start address >> 4) in bits 0-13, the constant LBO above it.
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer: the whole warp walks the (warp-uniform) loops so that
+    // descriptors, barrier addresses and ring state live in uniform registers, and one elected lane issues
+    // tcgen05.mma / tcgen05.commit.  (A single thread behind `if (lane == 0)` makes the compiler wrap every
+    // uniform-datapath instruction in an R2UR + vote retry loop; measured on the 384/768-channel layers that
+    // costs ~130 cycles per tap - 1.30 -> 1.47 PFLOP/s on the 768-channel k = 11 layer once removed.)
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t desc0 = make_smem_desc(0, 128, 0);
       const uint32_t dhi = (uint32_t)(desc0 >> 32);
@@ -236,46 +236,25 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               tc_fence_after();
             }
             const uint32_t a_lo = a_lo0 + as * (uint32_t)(U2_SLOT_BYTES >> 4);
-            if (nkk == 2) {
-              asm volatile(
-                  "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-                  "setp.ne.b32 p, %4, 0;\n\t"
-                  "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-                  "add.u64 da, da, 2;\n\tadd.u64 db, db, 2;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t}" ::"r"(d_tmem),
-                  "r"(a_lo), "r"(b_lo), "r"(dhi), "r"(accum), "r"(idesc)
-                  : "memory");
-            } else if (nkk == 4) {
-              asm volatile(
-                  "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-                  "setp.ne.b32 p, %4, 0;\n\t"
-                  "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-                  "add.u64 da, da, 2;\n\tadd.u64 db, db, 2;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t"
-                  "add.u64 da, da, 2;\n\tadd.u64 db, db, 2;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t"
-                  "add.u64 da, da, 2;\n\tadd.u64 db, db, 2;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t}" ::"r"(d_tmem),
-                  "r"(a_lo), "r"(b_lo), "r"(dhi), "r"(accum), "r"(idesc)
-                  : "memory");
-            } else {
+            if (elect_one()) {
               const uint64_t da = ((uint64_t)dhi << 32) | a_lo, db = ((uint64_t)dhi << 32) | b_lo;
               umma_f16_ss(d_tmem, da, db, idesc, accum);
               for (int kk = 1; kk < nkk; ++kk) umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, 1u);
+              if (!resident) umma_commit(&a_empty[as]);
             }
+            __syncwarp();
             accum = 1;
-            if (!resident) umma_commit(&a_empty[as]);
             if (++as == a_stages) { as = 0; aph ^= 1; }
           }
-          umma_commit(&x_empty[xs]);
+          if (elect_one()) umma_commit(&x_empty[xs]);
+          __syncwarp();
           if (++xs == U2_X_STAGES) { xs = 0; xph ^= 1; }
         }
-        umma_commit(&t_full[acc]);
+        if (elect_one()) umma_commit(&t_full[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
-      if (dbg) { p.dbg[U2D_MMA_TEMPTY] = w0; p.dbg[U2D_MMA_XFULL] = w1; p.dbg[U2D_MMA_AFULL] = w2; }
+      if (dbg && lane == 0) { p.dbg[U2D_MMA_TEMPTY] = w0; p.dbg[U2D_MMA_XFULL] = w1; p.dbg[U2D_MMA_AFULL] = w2; }
     }
   } else if (warp == 12) {
     if (lane == 0) {

@@ -334,8 +334,9 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (as conv_umma2.cu; N is always 256 here)
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer: the whole warp walks the (warp-uniform) loops so
+    // that descriptors and barrier addresses live in uniform registers; one elected lane issues tcgen05.mma / commit
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t desc0 = make_smem_desc(0, 128, 0);
       const uint32_t dhi = (uint32_t)(desc0 >> 32);
@@ -364,17 +365,22 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
               tc_fence_after();
             }
             const uint32_t a_lo = a_lo0 + as * (uint32_t)(UA_SLOT_BYTES >> 4);
-            const uint64_t da = ((uint64_t)dhi << 32) | a_lo, db = ((uint64_t)dhi << 32) | b_lo;
-            umma_f16_ss(d_tmem, da, db, idesc, accum);
-            for (int kk = 1; kk < nkk; ++kk) umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, 1u);
+            if (elect_one()) {
+              const uint64_t da = ((uint64_t)dhi << 32) | a_lo, db = ((uint64_t)dhi << 32) | b_lo;
+              umma_f16_ss(d_tmem, da, db, idesc, accum);
+              for (int kk = 1; kk < nkk; ++kk) umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, 1u);
+              if (!resident) umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
             accum = 1;
-            if (!resident) umma_commit(&a_empty[as]);
             if (++as == a_stages) { as = 0; aph ^= 1; }
           }
-          umma_commit(&x_empty[xs]);
+          if (elect_one()) umma_commit(&x_empty[xs]);
+          __syncwarp();
           if (++xs == UA_X_STAGES) { xs = 0; xph ^= 1; }
         }
-        umma_commit(&t_full[acc]);
+        if (elect_one()) umma_commit(&t_full[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
     }
