@@ -161,8 +161,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const long long t_start = dbg ? clock64() : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------ activation tiles
+    {
+      // ------------------------------------------------ activation tiles (whole warp in the loop, one elected lane issues)
       const uint32_t xbox_bytes = (uint32_t)p.x_box_rows * 128u;
       uint32_t xs = 0, xph = 0;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -170,17 +170,20 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int trow = t.t0 - p.center * p.dil;
         for (int c = 0; c < p.nchunks; ++c) {
           u2_wait(&x_empty[xs], xph ^ 1, dbg, w0);
-          mbar_expect_tx(&x_full[xs], (uint32_t)p.x_nbox * xbox_bytes);
-          unsigned char* dstx = x_st + xs * U2_X_STAGE_BYTES;
-          for (int q = 0; q < p.x_nbox; ++q)
-            tma_load_3d(dstx + q * xbox_bytes, &tmap_x, c * 64, trow + q * p.x_box_rows, t.b, &x_full[xs]);
+          if (elect_one()) {
+            mbar_expect_tx(&x_full[xs], (uint32_t)p.x_nbox * xbox_bytes);
+            unsigned char* dstx = x_st + xs * U2_X_STAGE_BYTES;
+            for (int q = 0; q < p.x_nbox; ++q)
+              tma_load_3d(dstx + q * xbox_bytes, &tmap_x, c * 64, trow + q * p.x_box_rows, t.b, &x_full[xs]);
+          }
+          __syncwarp();
           if (++xs == U2_X_STAGES) { xs = 0; xph ^= 1; }
         }
       }
-      if (dbg) p.dbg[U2D_X_EMPTY] = w0;
+      if (dbg && lane == 0) p.dbg[U2D_X_EMPTY] = w0;
     }
   } else if (warp == 10 || warp == 11) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------ weight tiles: this warp owns every second ring stage
       const uint32_t mine = (uint32_t)(warp - 10);
       const uint32_t a_bytes = (uint32_t)p.wrows * 128u;
@@ -192,14 +195,17 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           for (int j = 0; j < p.k; ++j, ++n) {
             if ((n & 1u) == mine) {
               u2_wait(&a_empty[as], aph ^ 1, dbg, w0);
-              mbar_expect_tx(&a_full[as], a_bytes);
-              tma_load_3d(a_st + as * U2_SLOT_BYTES, &tmap_w, c * 64, cot * CW, j, &a_full[as]);
+              if (elect_one()) {
+                mbar_expect_tx(&a_full[as], a_bytes);
+                tma_load_3d(a_st + as * U2_SLOT_BYTES, &tmap_w, c * 64, cot * CW, j, &a_full[as]);
+              }
+              __syncwarp();
             }
             if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
           }
         }
       }
-      if (dbg) p.dbg[U2D_A_EMPTY0 + mine] = w0;
+      if (dbg && lane == 0) p.dbg[U2D_A_EMPTY0 + mine] = w0;
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer: the whole warp walks the (warp-uniform) loops so that
@@ -257,8 +263,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (dbg && lane == 0) { p.dbg[U2D_MMA_TEMPTY] = w0; p.dbg[U2D_MMA_XFULL] = w1; p.dbg[U2D_MMA_AFULL] = w2; }
     }
   } else if (warp == 12) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------ output stores: block cb leaves from staging buffer cb & 1
+      // (one elected lane issues; bulk async-groups are per thread and elect.sync is deterministic for a given
+      //  member mask, so the same lane commits and waits every time)
       uint32_t cb = 0;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const U2Tile t = u2_tile(p, tile);
@@ -266,20 +274,27 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           const uint32_t ob = cb & 1u;
           if (cb >= 1) {                       // hand the previous block's buffer back as soon as it has been read
             const long long tr = dbg ? clock64() : 0;
-            bulk_wait_group_read<0>();
+            if (elect_one()) {
+              bulk_wait_group_read<0>();
+              mbar_arrive(&out_free[ob ^ 1u]);
+            }
+            __syncwarp();
             if (dbg) w1 += clock64() - tr;
-            mbar_arrive(&out_free[ob ^ 1u]);
           }
           u2_wait(&out_ready[ob], (cb >> 1) & 1u, dbg, w0);
-          tma_store_3d(&tmap_out, out_st + ob * U2_SLOT_BYTES, t.cot * CW, t.t0 + nb, t.b);
-          bulk_commit_group();
+          if (elect_one()) {
+            tma_store_3d(&tmap_out, out_st + ob * U2_SLOT_BYTES, t.cot * CW, t.t0 + nb, t.b);
+            bulk_commit_group();
+          }
+          __syncwarp();
         }
       }
-      bulk_wait_group<0>();
-      if (dbg) { p.dbg[U2D_ST_READY] = w0; p.dbg[U2D_ST_READ] = w1; }
+      __syncwarp();
+      if (elect_one()) bulk_wait_group<0>();
+      if (dbg && lane == 0) { p.dbg[U2D_ST_READY] = w0; p.dbg[U2D_ST_READ] = w1; }
     }
   } else if (warp == 13) {
-    if (NIN >= 1 && lane == 0) {
+    if (NIN >= 1) {
       // ------------------------------------------------ residual / accumulate rows, 3 blocks ahead of the math warps
       const uint32_t in_bytes = (uint32_t)(CB * CW * 4 * NIN);
       uint32_t cb = 0;
@@ -288,13 +303,16 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int nb = 0; nb < t.nb_end; nb += CB, ++cb) {
           const uint32_t slot = cb % U2_IN_SLOTS;
           u2_wait(&in_free[slot], ((cb / U2_IN_SLOTS) & 1u) ^ 1u, dbg, w0);
-          unsigned char* dst = in_st + slot * U2_SLOT_BYTES;
-          mbar_expect_tx(&in_full[slot], in_bytes);
-          tma_load_3d(dst, &tmap_res, t.cot * CW, t.t0 + nb, t.b, &in_full[slot]);
-          if (NIN == 2) tma_load_3d(dst + CB * CW * 4, &tmap_acc, t.cot * CW, t.t0 + nb, t.b, &in_full[slot]);
+          if (elect_one()) {
+            unsigned char* dst = in_st + slot * U2_SLOT_BYTES;
+            mbar_expect_tx(&in_full[slot], in_bytes);
+            tma_load_3d(dst, &tmap_res, t.cot * CW, t.t0 + nb, t.b, &in_full[slot]);
+            if (NIN == 2) tma_load_3d(dst + CB * CW * 4, &tmap_acc, t.cot * CW, t.t0 + nb, t.b, &in_full[slot]);
+          }
+          __syncwarp();
         }
       }
-      if (dbg) p.dbg[U2D_IN_FREE] = w0;
+      if (dbg && lane == 0) p.dbg[U2D_IN_FREE] = w0;
     }
   } else {
     // ------------------------------------------------ epilogue math warps 2..9

@@ -152,7 +152,7 @@ __device__ __forceinline__ void ua_segment(const UAParams& p, uint32_t taddr, in
     }
     if (j >= 1 && rpos == 0) {
       // the buffer about to be written was handed to the TMA two rounds ago
-      if (lane == 0) bulk_wait_group_read<1>();
+      if (elect_one()) bulk_wait_group_read<1>();   // elect.sync is deterministic: the same lane owns all bulk groups
       __syncwarp();
       obuf = stg + (nstore & 1u) * UA_STAGE_BYTES;
     }
@@ -241,7 +241,7 @@ __device__ __forceinline__ void ua_segment(const UAParams& p, uint32_t taddr, in
         rpos = 0;
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           const int rowA = tseg + round * Rs;    // rows >= T are clipped by the tensor map
           ua_tma_store(omap, obuf, ch0, rowA, b);
           if (rowA + L < T) ua_tma_store(omap, obuf + half_bytes, ch0, rowA + L, b);
@@ -295,7 +295,7 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   const int CW = p.CW;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------ activation tiles (rows t0-6-center*dil ...; TMA zero fill = conv padding)
       const uint32_t xbox_bytes = (uint32_t)p.x_box_rows * 128u;
       uint32_t xs = 0, xph = 0;
@@ -304,16 +304,19 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int trow = t.t0 - UA_LEAD - p.center * p.dil;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(&x_empty[xs], xph ^ 1);
-          mbar_expect_tx(&x_full[xs], (uint32_t)p.x_nbox * xbox_bytes);
-          unsigned char* dstx = x_st + xs * UA_X_STAGE_BYTES;
-          for (int q = 0; q < p.x_nbox; ++q)
-            tma_load_3d(dstx + q * xbox_bytes, &tmap_x, c * 64, trow + q * p.x_box_rows, t.b, &x_full[xs]);
+          if (elect_one()) {
+            mbar_expect_tx(&x_full[xs], (uint32_t)p.x_nbox * xbox_bytes);
+            unsigned char* dstx = x_st + xs * UA_X_STAGE_BYTES;
+            for (int q = 0; q < p.x_nbox; ++q)
+              tma_load_3d(dstx + q * xbox_bytes, &tmap_x, c * 64, trow + q * p.x_box_rows, t.b, &x_full[xs]);
+          }
+          __syncwarp();
           if (++xs == UA_X_STAGES) { xs = 0; xph ^= 1; }
         }
       }
     }
   } else if (warp == 10 || warp == 11) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------ weight tiles: this warp owns every second ring stage
       const uint32_t mine = (uint32_t)(warp - 10);
       const uint32_t a_bytes = (uint32_t)p.wrows * 128u;
@@ -325,8 +328,11 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           for (int j = 0; j < p.k; ++j, ++n) {
             if ((n & 1u) == mine) {
               mbar_wait(&a_empty[as], aph ^ 1);
-              mbar_expect_tx(&a_full[as], a_bytes);
-              tma_load_3d(a_st + as * UA_SLOT_BYTES, &tmap_w, c * 64, cot * CW, j, &a_full[as]);
+              if (elect_one()) {
+                mbar_expect_tx(&a_full[as], a_bytes);
+                tma_load_3d(a_st + as * UA_SLOT_BYTES, &tmap_w, c * 64, cot * CW, j, &a_full[as]);
+              }
+              __syncwarp();
             }
             if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
           }
@@ -428,7 +434,8 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       if (lane == 0) mbar_arrive(&t_empty[acc]);
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
-    if (lane == 0) bulk_wait_group<0>();
+    __syncwarp();
+    if (elect_one()) bulk_wait_group<0>();
   }
 
   tc_fence_before();
