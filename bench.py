@@ -319,7 +319,7 @@ def main():
     a_ms, a_bytes, a_n = prof["activation"]
     o_ms, _, o_n = prof["other"]
     tot = c_ms + s_ms + a_ms + o_ms
-    conv_ms, conv_flops, conv_n, conv_name = (c_ms, c_flops, c_n, "conv_umma_kernel (tcgen05 implicit-GEMM Conv1d/ConvTranspose1d)") \
+    conv_ms, conv_flops, conv_n, conv_name = (c_ms, c_flops, c_n, "conv_umma2_kernel + conv_umma2a_kernel (tcgen05 implicit-GEMM Conv1d/ConvTranspose1d; the a-variant carries the following Activation1d in its epilogue)") \
         if c_n else (s_ms, s_flops, s_n, "conv_simt_kernel (fp32)")
     tensor_peak = pk["bf16_tflops_sustained"]
     ach_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -329,7 +329,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
                 "share_of_step": round(conv_ms / tot, 3) if tot else None, "launches": conv_n,
                 "avg_launch_ms": round(conv_ms / max(conv_n, 1), 4)}
-    roofline_act = {"kernel": "act1d_cl_kernel (fused up2-snakebeta-down2, channels-last)", "bound": "hbm",
+    roofline_act = {"kernel": "act1d_cl_packed_kernel (stand-alone fused up2-snakebeta-down2, channels-last; the activations fused into conv epilogues are not counted here)", "bound": "hbm",
                     "achieved": round(ach_gb, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": None,
                     "share_of_step": round(a_ms / tot, 3) if tot else None, "launches": a_n}

@@ -141,3 +141,23 @@ def test_act1d_errors_and_empty(ops, act_mod):
         ops.act1d(torch.zeros(2, 3, 8, device=DEV), a, a, taps[:6], taps, False)
     with pytest.raises(NotImplementedError):
         act_mod.Activation1d(act_mod.SnakeBeta(3), up_ratio=4)
+
+
+def test_act1d_fp32_large_arguments(ops):
+    """the accurate snake (3-term Cody-Waite reduction mod pi + degree-9 polynomial, csrc/common.cuh sin_mod_pi)
+    keeps the <= 1e-5 relative bar when a*u reaches the thousands (large activations times exp(alpha) ~ 30)."""
+    g = torch.Generator().manual_seed(11)
+    B, C, T = 2, 6, 4096
+    x = torch.randn(B, C, T, generator=g) * 30.0
+    a = torch.full((C,), 3.4) + torch.randn(C, generator=g) * 0.05      # exp(3.4) = 30
+    b = torch.randn(C, generator=g) * 0.5 + 3.0                          # keeps the sin^2 term O(1)
+    taps = O.kaiser_taps()
+    ref = O.activation1d(x.double(), a.double(), b.double(), taps.double(), taps.double())
+    assert float((x.abs().max() * a.exp().max())) > 2000.0
+    for layout in ("bct", "cl"):
+        if layout == "bct":
+            y = ops.act1d(x.to(DEV), a.to(DEV), b.to(DEV), taps.tolist(), taps.tolist(), False).cpu()
+        else:
+            y = ops.act1d_cl(x.transpose(1, 2).contiguous().to(DEV), a.to(DEV), b.to(DEV), taps.tolist(), taps.tolist(),
+                             False, False).cpu().transpose(1, 2)
+        assert (y.double() - ref).abs().max() <= 1e-5 * float(ref.abs().max()), layout

@@ -83,14 +83,13 @@ struct VecIO<__nv_bfloat16, 2> {
   }
 
 template <typename Tin, typename Tout, int VEC, bool FAST>
-__global__ void __launch_bounds__(128)
-act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
-                const float* __restrict__ beta_log, const Taps taps, int B, int64_t T, int C, int L,
-                int nseg, int nseg_head, int64_t tail_start, int64_t nitems) {
-  // this launch covers `nseg` segments of length L per utterance: `nseg_head` segments from
-  // row 0 and the rest from row `tail_start` (the rows in between belong to the packed kernel)
+__device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin* __restrict__ src,
+                                              const float* __restrict__ alpha_log, const float* __restrict__ beta_log,
+                                              const Taps& taps, int B, int64_t T, int C, int L, int nseg, int nseg_head,
+                                              int64_t tail_start, int64_t nitems, int64_t item) {
+  // `nseg` segments of length L per utterance: `nseg_head` segments from row 0 and the rest from row
+  // `tail_start` (the rows in between belong to the packed path)
   const int P = C / VEC;
-  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= nitems) return;
   const int pair = (int)(item % P);
   const int64_t rest = item / P;
@@ -209,6 +208,15 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
   }
 }
 
+template <typename Tin, typename Tout, int VEC, bool FAST>
+__global__ void __launch_bounds__(128)
+act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
+                const float* __restrict__ beta_log, const Taps taps, int B, int64_t T, int C, int L,
+                int nseg, int nseg_head, int64_t tail_start, int64_t nitems) {
+  act1d_cl_body<Tin, Tout, VEC, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, L, nseg, nseg_head, tail_start, nitems,
+                                      (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Packed variant (2 channels per thread as one f32x2 lane pair): Blackwell's FFMA2
 // (fma.rn.f32x2) does two FMAs per issue slot.  ncu showed the scalar kernel is
@@ -266,7 +274,15 @@ template <typename Tin, typename Tout, bool FAST>
 __global__ void __launch_bounds__(kPackedThreads)
 act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
                        const float* __restrict__ beta_log, const TapsPacked tp, int B, int64_t T, int C, int L,
-                       int nseg_int, int head_len, int64_t nitems) {
+                       int nseg_int, int head_len, int64_t nitems, const Taps taps, int main_blocks, int nseg_edge,
+                       int nseg_head, int64_t tail_start, int64_t nitems_edge) {
+  if ((int)blockIdx.x >= main_blocks) {
+    // the last blocks of the grid take the sequence ends (short segments, scalar edge-aware path): they run
+    // beside the interior blocks instead of as a separate ~10 us launch behind them
+    act1d_cl_body<Tin, Tout, 2, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, head_len, nseg_edge, nseg_head, tail_start,
+                                      nitems_edge, (int64_t)(blockIdx.x - main_blocks) * blockDim.x + threadIdx.x);
+    return;
+  }
   const int P = C / 2;
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= nitems) return;
@@ -351,28 +367,30 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
   // interior segments: kEdge + s*L + L + 4 + 12 (prefetch run-ahead) <= T - 1
   int64_t n_int = (T - 5 - 12 - kEdge) / L;
   if (n_int < 0) n_int = 0;
-  if (n_int > 0) {
-    TapsPacked tp;
-    make_taps_packed(&tp, taps);
-    const int64_t nitems = (int64_t)B * n_int * P;
-    const int64_t blocks = ceil_div(nitems, kPackedThreads);
-    if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
-    act1d_cl_packed_kernel<Tin, Tout, FAST><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
-        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, L, (int)n_int, kEdge, nitems);
-    BVG_LAUNCHED();
-  }
   // edges: head [0, kEdge) (or everything when there is no interior) and tail [tail_start, T)
   const int64_t tail_start = n_int > 0 ? kEdge + n_int * L : T;
   const int64_t head_end = n_int > 0 ? kEdge : T;
   const int nseg_head = (int)ceil_div(head_end, kEdge);
   const int nseg_tail = (int)ceil_div(T - tail_start, kEdge);
   const int nseg = nseg_head + nseg_tail;
-  const int64_t nitems = (int64_t)B * nseg * P;
-  const int64_t blocks = ceil_div(nitems, threads);
+  const int64_t nitems_edge = (int64_t)B * nseg * P;
+  if (n_int > 0) {
+    TapsPacked tp;
+    make_taps_packed(&tp, taps);
+    const int64_t nitems = (int64_t)B * n_int * P;
+    const int64_t main_blocks = ceil_div(nitems, kPackedThreads);
+    const int64_t blocks = main_blocks + ceil_div(nitems_edge, kPackedThreads);
+    if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
+    act1d_cl_packed_kernel<Tin, Tout, FAST><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
+        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
+        nseg, nseg_head, tail_start, nitems_edge);
+    BVG_LAUNCHED();
+    return BVG_OK;
+  }
+  const int64_t blocks = ceil_div(nitems_edge, threads);
   if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
   act1d_cl_kernel<Tin, Tout, 2, FAST><<<(unsigned)blocks, threads, 0, st>>>(
-      (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, kEdge, nseg, nseg_head,
-      n_int > 0 ? tail_start : T, nitems);
+      (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, kEdge, nseg, nseg_head, T, nitems_edge);
   BVG_LAUNCHED();
   return BVG_OK;
 }

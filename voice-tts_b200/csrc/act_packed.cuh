@@ -51,7 +51,7 @@ struct SnakePair {
     } else {
       float u0, u1;
       upk2(u, u0, u1);
-      const float s0 = sinf(u0 * a0), s1 = sinf(u1 * a1);
+      const float s0 = sin_mod_pi(u0 * a0), s1 = sin_mod_pi(u1 * a1);
       return pk2(fmaf(ib0 * s0, s0, u0), fmaf(ib1 * s1, s1, u1));
     }
   }
@@ -68,7 +68,7 @@ __device__ __forceinline__ float snake_apply(float u, float a, float ib) {
     const float z = fmaf(2.0f * a, u, -2.0f * a * hb);
     return fmaf(-hb, __cosf(z), u);
   } else {
-    const float s = sinf(u * a);
+    const float s = sin_mod_pi(u * a);
     return fmaf(ib * s, s, u);
   }
 }

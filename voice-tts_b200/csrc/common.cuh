@@ -87,8 +87,25 @@ __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// sin(x) up to sign: sin(x - k*pi) with k = rint(x / pi).  The snake only uses sin^2, so the (-1)^k is never
+// needed.  3-term Cody-Waite reduction (the products k*PI_HI, k*PI_MID are exact for |x| < ~1e4) and a degree-9
+// odd minimax polynomial on [-pi/2, pi/2]: absolute error <= 1.2e-7 (fp32 rounding limited) for |x| <= 1e4,
+// growing as ~|x| * 1e-11 beyond; no MUFU, no branch, no local-memory frame (libdevice sinf drags its
+// Payne-Hanek slow path - 32 bytes of stack and ~25 registers - into every kernel that calls it).
+__device__ __forceinline__ float sin_mod_pi(float x) {
+  const float k = rintf(x * 0.318309886f);
+  float r = fmaf(k, -3.140625f, x);
+  r = fmaf(k, -9.67502593994140625e-4f, r);
+  r = fmaf(k, -1.509957990978376432e-7f, r);
+  const float s = r * r;
+  float p = fmaf(2.5931510663212975e-06f, s, -0.00019803375471383333f);
+  p = fmaf(p, s, 0.008332970552146435f);
+  p = fmaf(p, s, -0.16666655242443085f);
+  return fmaf(r * s, p, r);
+}
+
 // SnakeBeta on one upsampled sample: u + inv_b * sin(a*u)^2.
-//   ACCURATE: libdevice sinf (<= 1 ulp-ish; full range reduction) - fp32 parity mode
+//   ACCURATE: sin_mod_pi (<= 1.2e-7 absolute) - fp32 parity mode
 //   fast    : sin^2(z) = 0.5 - 0.5*cos(2z); one MUFU.COS on a pre-scaled argument
 template <bool FAST>
 __device__ __forceinline__ float snake_eval(float u, float a, float inv_b) {
@@ -98,7 +115,7 @@ __device__ __forceinline__ float snake_eval(float u, float a, float inv_b) {
     float c = __cosf(2.0f * a * u);
     return fmaf(-0.5f * inv_b, c, fmaf(0.5f, inv_b, u));
   } else {
-    float s = sinf(u * a);
+    float s = sin_mod_pi(u * a);
     return fmaf(inv_b * s, s, u);
   }
 }

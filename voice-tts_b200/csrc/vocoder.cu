@@ -75,9 +75,13 @@ struct bvg_vocoder {
   void* dev_wav = nullptr;  size_t dev_wav_bytes = 0;
   int last_launches = 0;
   // per-kernel CUDA-event profiling (option "profile"): category -> accumulated work; events resolved on read
-  struct ProfRec { int cat; double work; cudaEvent_t e0, e1; int cin, cout, k, dil; long long rows; };
+  // consecutive launches on one stream share the boundary event (end of launch i = start of launch i+1)
+  struct ProfRec { int cat; double work; int i0, i1; int cin, cout, k, dil; long long rows; };
   int opt_profile = 0;
   std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_ev;      // events of the current window, indexed by ProfRec::i0/i1
+  int prof_last = -1;                    // index of the last boundary event, -1: none
+  cudaStream_t prof_last_stream = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int>> graphs;  // exec + kernels inside
 };
@@ -192,18 +196,28 @@ static cudaEvent_t prof_event(bvg_vocoder* v) {
   return e;
 }
 struct ProfScope {
-  bvg_vocoder* v; cudaStream_t st; int cat; double work; cudaEvent_t e0 = nullptr;
+  bvg_vocoder* v; cudaStream_t st; int cat; double work; int i0 = -1;
   int cin = 0, cout = 0, k = 0, dil = 0; long long rows = 0;
   ProfScope(bvg_vocoder* v_, cudaStream_t st_, int cat_, double work_) : v(v_), st(st_), cat(cat_), work(work_) {
-    if (v->opt_profile) { e0 = prof_event(v); cudaEventRecord(e0, st); }
-  }
-  ~ProfScope() {
-    if (e0) {
-      cudaEvent_t e1 = prof_event(v); cudaEventRecord(e1, st);
-      v->prof.push_back({cat, work, e0, e1, cin, cout, k, dil, rows});
+    if (!v->opt_profile) return;
+    if (v->prof_last >= 0 && v->prof_last_stream == st) {
+      i0 = v->prof_last;                 // nothing was enqueued on this stream since the previous launch ended
+    } else {
+      cudaEvent_t e = prof_event(v); cudaEventRecord(e, st);
+      v->prof_ev.push_back(e); i0 = (int)v->prof_ev.size() - 1;
     }
   }
+  ~ProfScope() {
+    if (i0 < 0) return;
+    cudaEvent_t e = prof_event(v); cudaEventRecord(e, st);
+    v->prof_ev.push_back(e);
+    const int i1 = (int)v->prof_ev.size() - 1;
+    v->prof.push_back({cat, work, i0, i1, cin, cout, k, dil, rows});
+    v->prof_last = i1; v->prof_last_stream = st;
+  }
 };
+// anything enqueued outside a ProfScope (copies, event waits, graph launches) breaks the chain of shared events
+static inline void prof_break(bvg_vocoder* v) { v->prof_last = -1; }
 
 static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, void* out, int out_dt,
                     const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st) {
@@ -331,6 +345,7 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
       cudaStream_t sj = (nb > 1 && j != v->nk - 1) ? v->aux[slot] : st;
       static const bool dbg_one_aux = getenv("BVG_DBG_ONE_AUX") != nullptr;   // debug: all aux blocks on aux[0], own buffers
       if (dbg_one_aux && sj != st) sj = v->aux[0];
+      if (nb > 1) prof_break(v);
       if (sj != st) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_fork, 0));
       static const int dbg_serial = getenv("BVG_SERIAL_BLOCKS") ? atoi(getenv("BVG_SERIAL_BLOCKS")) : 0;   // debug: bit j = block j starts after block j-1
       if (((dbg_serial >> j) & 1) && nb > 1 && j > 0) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0));
@@ -359,7 +374,7 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
           g_dbg.add(bf.y[slot], nel * 4, "y", i, j, l, sj);
         } else {
           const bool to_next = (j == v->nk - 1) && !last_stage;
-          if (nb > 1 && j > 0) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0));   // XS of block j-1
+          if (nb > 1 && j > 0) { prof_break(v); BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0)); }   // XS of block j-1
           rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, to_next ? bf.nx : (void*)bf.xs, to_next ? adt : BVG_F32, cur,
                         j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, sj);
           if (rc) return rc;
@@ -443,6 +458,7 @@ int vocoder_forward(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, in
   int rc = ensure_device_ok();
   if (rc) return rc;
   const uint64_t l0 = g_launches.load();
+  prof_break(v);   // the caller may have enqueued work on `st` since the last forward
   const int mb = max_microbatch(v, B, T0);
   rc = ensure_arena(v, plan_buffers(v, mb, T0, nullptr));
   if (rc) return rc;
@@ -752,7 +768,7 @@ extern "C" void bvg_destroy(bvg_vocoder* v) {
   for (auto& a : v->acts) free_act(a);
   free_act(v->act_post);
   if (v->post_w) cudaFree(v->post_w);
-  for (auto& r : v->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto& e : v->prof_ev) cudaEventDestroy(e);
   for (auto& e : v->ev_pool) cudaEventDestroy(e);
   for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
   if (v->arena) cudaFree(v->arena);
@@ -805,7 +821,7 @@ extern "C" int bvg_profile_dump(bvg_vocoder* v, const char* path) {
   fprintf(f, "cat,cin,cout,k,dil,rows,ms,work,rate\n");
   for (auto& r : v->prof) {
     float t = 0.f;
-    cudaEventElapsedTime(&t, r.e0, r.e1);
+    cudaEventElapsedTime(&t, v->prof_ev[r.i0], v->prof_ev[r.i1]);
     fprintf(f, "%d,%d,%d,%d,%d,%lld,%.4f,%.4g,%.4g\n", r.cat, r.cin, r.cout, r.k, r.dil, r.rows, t, r.work,
             t > 0 ? r.work / (t * 1e-3) : 0.0);
   }
@@ -824,12 +840,14 @@ extern "C" int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double
   for (auto& r : v->prof) {
     if (r.cat != category) continue;
     float t = 0.f;
-    BVG_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    BVG_CUDA(cudaEventElapsedTime(&t, v->prof_ev[r.i0], v->prof_ev[r.i1]));
     *ms += t; *work += r.work; *launches += 1;
   }
   if (category == CAT_N - 1) {
-    for (auto& r : v->prof) { v->ev_pool.push_back(r.e0); v->ev_pool.push_back(r.e1); }
+    for (auto& e : v->prof_ev) v->ev_pool.push_back(e);
+    v->prof_ev.clear();
     v->prof.clear();
+    v->prof_last = -1;
   }
   return BVG_OK;
 }
