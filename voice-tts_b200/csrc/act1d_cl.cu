@@ -85,7 +85,7 @@ struct VecIO<__nv_bfloat16, 2> {
 template <typename Tin, typename Tout, int VEC, bool FAST>
 __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin* __restrict__ src,
                                               const float* __restrict__ alpha_log, const float* __restrict__ beta_log,
-                                              const Taps& taps, int B, int64_t T, int C, int L, int nseg, int nseg_head,
+                                              const Taps& taps, int B, int64_t T, int C, int ld, int L, int nseg, int nseg_head,
                                               int64_t tail_start, int64_t nitems, int64_t item) {
   // `nseg` segments of length L per utterance: `nseg_head` segments from row 0 and the rest from row
   // `tail_start` (the rows in between belong to the packed path)
@@ -104,8 +104,8 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
     ib[j] = 1.0f / (expf(__ldg(beta_log + c0 + j)) + 1e-9f);
   }
 
-  const Tin* sp = src + (int64_t)b * T * C + c0;
-  Tout* dp = dst + (int64_t)b * T * C + c0;
+  const Tin* sp = src + (int64_t)b * T * ld + c0;
+  Tout* dp = dst + (int64_t)b * T * ld + c0;
   const bool head = seg < nseg_head;
   const int64_t t0 = head ? (int64_t)seg * L : tail_start + (int64_t)(seg - nseg_head) * L;
   const int64_t rend = head ? (tail_start < T ? tail_start : T) : T;   // end of this segment's region
@@ -118,13 +118,13 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
   // steps run over t = t0-5 .. t1-1; step t loads x[t+5] and produces v[2t+5], v[2t+6], y[t].
   if (t0 >= 5 && t0 + L + 4 <= tlast && t1 - t0 == L) {
     // ---- interior segment (L = 6n-5): no clamps, no edge fixes, no predicates ----
-    const Tin* lp = sp + (t0 - 5) * C;
-    Tout* op = dp + t0 * C;
+    const Tin* lp = sp + (t0 - 5) * ld;
+    Tout* op = dp + t0 * ld;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { VecIO<Tin, VEC>::load(lp, X[i]); lp += C; }
+    for (int i = 0; i < 5; ++i) { VecIO<Tin, VEC>::load(lp, X[i]); lp += ld; }
     float XN[6][VEC];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { VecIO<Tin, VEC>::load(lp, XN[i]); lp += C; }
+    for (int i = 0; i < 6; ++i) { VecIO<Tin, VEC>::load(lp, XN[i]); lp += ld; }
     // first body: 5 warm-up steps (no output) + 1 full step
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
@@ -138,14 +138,14 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
         float y[VEC];
         BVG_ACT_DOWN(s, V, taps, y)
         VecIO<Tout, VEC>::store(op, y);
-        op += C;
+        op += ld;
       }
     }
     const int nbody = (L + 5) / 6 - 1;
     for (int it = 0; it < nbody; ++it) {
       // loads of this body: issued up front, consumed step by step
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { VecIO<Tin, VEC>::load(lp, XN[i]); lp += C; }
+      for (int i = 0; i < 6; ++i) { VecIO<Tin, VEC>::load(lp, XN[i]); lp += ld; }
 #pragma unroll
       for (int s = 0; s < 6; ++s) {
 #pragma unroll
@@ -156,7 +156,7 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
         for (int j = 0; j < VEC; ++j) { V[(2 * s + 10) % 12][j] = vo[j]; V[(2 * s + 11) % 12][j] = ve[j]; }
         BVG_ACT_DOWN(s, V, taps, y)
         VecIO<Tout, VEC>::store(op, y);
-        op += C;
+        op += ld;
       }
     }
     return;
@@ -170,7 +170,7 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
   for (int i = 0; i < 5; ++i) {
     int64_t ti = t0 - 5 + i;
     ti = ti < 0 ? 0 : (ti > tlast ? tlast : ti);
-    VecIO<Tin, VEC>::load(sp + ti * C, X[i]);
+    VecIO<Tin, VEC>::load(sp + ti * ld, X[i]);
   }
   const int nsteps = (int)(t1 - t0) + 5;
   for (int base = 0; base < nsteps; base += 6) {
@@ -179,7 +179,7 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
       const int64_t t = t0 - 5 + base + s;
       int64_t tl = t + 5;
       tl = tl > tlast ? tlast : tl;  // t+5 >= 0 always
-      VecIO<Tin, VEC>::load(sp + tl * C, X[(s + 5) % 6]);
+      VecIO<Tin, VEC>::load(sp + tl * ld, X[(s + 5) % 6]);
       float vo[VEC], ve[VEC];
       BVG_ACT_UP(s, X, taps, a, ib, vo, ve)
       // right edge: v[m >= 2T] := v[2T-1]; v[2T-1] is the odd sample of step T-3
@@ -203,7 +203,7 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
       }
       float y[VEC];
       BVG_ACT_DOWN(s, V, taps, y)
-      if (t >= t0 && t < t1) VecIO<Tout, VEC>::store(dp + t * C, y);
+      if (t >= t0 && t < t1) VecIO<Tout, VEC>::store(dp + t * ld, y);
     }
   }
 }
@@ -211,9 +211,9 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
 template <typename Tin, typename Tout, int VEC, bool FAST>
 __global__ void __launch_bounds__(128)
 act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
-                const float* __restrict__ beta_log, const Taps taps, int B, int64_t T, int C, int L,
+                const float* __restrict__ beta_log, const Taps taps, int B, int64_t T, int C, int ld, int L,
                 int nseg, int nseg_head, int64_t tail_start, int64_t nitems) {
-  act1d_cl_body<Tin, Tout, VEC, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, L, nseg, nseg_head, tail_start, nitems,
+  act1d_cl_body<Tin, Tout, VEC, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, L, nseg, nseg_head, tail_start, nitems,
                                       (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
@@ -261,7 +261,7 @@ template <> struct PairIO<__nv_bfloat16> {
       _Pragma("unroll") for (int k = 1; k < 12; ++k)                                       \
         acc = fma2(tp.d[k < 6 ? k : 11 - k], V[(2 * (S) + k) % 12], acc);                  \
       PairIO<Tout>::store(op, acc);                                                        \
-      op += C;                                                                             \
+      op += ld;                                                                             \
     }                                                                                      \
   }
 
@@ -273,13 +273,13 @@ constexpr int kPackedThreads = 128;
 template <typename Tin, typename Tout, bool FAST>
 __global__ void __launch_bounds__(kPackedThreads)
 act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
-                       const float* __restrict__ beta_log, const TapsPacked tp, int B, int64_t T, int C, int L,
+                       const float* __restrict__ beta_log, const TapsPacked tp, int B, int64_t T, int C, int ld, int L,
                        int nseg_int, int head_len, int64_t nitems, const Taps taps, int main_blocks, int nseg_edge,
                        int nseg_head, int64_t tail_start, int64_t nitems_edge) {
   if ((int)blockIdx.x >= main_blocks) {
     // the last blocks of the grid take the sequence ends (short segments, scalar edge-aware path): they run
     // beside the interior blocks instead of as a separate ~10 us launch behind them
-    act1d_cl_body<Tin, Tout, 2, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, head_len, nseg_edge, nseg_head, tail_start,
+    act1d_cl_body<Tin, Tout, 2, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, head_len, nseg_edge, nseg_head, tail_start,
                                       nitems_edge, (int64_t)(blockIdx.x - main_blocks) * blockDim.x + threadIdx.x);
     return;
   }
@@ -295,8 +295,8 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
   sn.init(__ldg(alpha_log + c0), __ldg(alpha_log + c0 + 1), __ldg(beta_log + c0), __ldg(beta_log + c0 + 1));
 
   const int64_t t0 = head_len + (int64_t)seg * L;   // interior region [head_len, head_len + nseg_int*L)
-  const Tin* lp = src + ((int64_t)b * T + (t0 - 5)) * C + c0;
-  Tout* op = dst + ((int64_t)b * T + t0) * C + c0;
+  const Tin* lp = src + ((int64_t)b * T + (t0 - 5)) * ld + c0;
+  Tout* op = dst + ((int64_t)b * T + t0) * ld + c0;
 
   f32x2 X[6], V[12];
   // Rolling prefetch: R[s] holds the raw row consumed by step s of the current 12-step
@@ -305,16 +305,16 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
   // interior region, so the run-ahead loads of the last segment stay inside the tensor.
   typename PairIO<Tin>::raw_t R[12];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) { X[i] = PairIO<Tin>::cvt(PairIO<Tin>::ldraw(lp)); lp += C; }
+  for (int i = 0; i < 5; ++i) { X[i] = PairIO<Tin>::cvt(PairIO<Tin>::ldraw(lp)); lp += ld; }
 #pragma unroll
-  for (int i = 0; i < 12; ++i) { R[i] = PairIO<Tin>::ldraw(lp); lp += C; }
+  for (int i = 0; i < 12; ++i) { R[i] = PairIO<Tin>::ldraw(lp); lp += ld; }
   const int niter = (L + 5) / 12;   // L = 12m-5
   // first iteration: steps 0..4 are warm-up (no output)
 #pragma unroll
   for (int s = 0; s < 12; ++s) {
     X[(s + 5) % 6] = PairIO<Tin>::cvt(R[s]);
     R[s] = PairIO<Tin>::ldraw(lp);
-    lp += C;
+    lp += ld;
     if (s < 5) BVG_ACT2_STEP(s, false) else BVG_ACT2_STEP(s, true)
   }
   for (int it = 1; it < niter; ++it) {
@@ -322,7 +322,7 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
     for (int s = 0; s < 12; ++s) {
       X[(s + 5) % 6] = PairIO<Tin>::cvt(R[s]);
       R[s] = PairIO<Tin>::ldraw(lp);
-      lp += C;
+      lp += ld;
       BVG_ACT2_STEP(s, true)
     }
   }
@@ -334,8 +334,9 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
 // threads are not a serial tail behind the main kernel.
 template <typename Tin, typename Tout, bool FAST>
 static int launch_cl(void* dst, const void* src, const float* alpha_log, const float* beta_log,
-                     const Taps& taps, int B, int64_t T, int C, cudaStream_t st) {
-  const bool vec2 = (C % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) % (2 * sizeof(Tin))) == 0) &&
+                     const Taps& taps, int B, int64_t T, int C, int ld, cudaStream_t st) {
+  // C channels of every row are processed; rows are ld >= C elements apart (pad channels are neither read nor written)
+  const bool vec2 = (C % 2 == 0) && (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) % (2 * sizeof(Tin))) == 0) &&
                     ((reinterpret_cast<uintptr_t>(dst) % (2 * sizeof(Tout))) == 0);
   const int threads = 128;
   constexpr int kEdge = 13;   // 6n-5, >= 5
@@ -350,7 +351,7 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
     const int64_t blocks = ceil_div(nitems, threads);
     if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
     act1d_cl_kernel<Tin, Tout, 1, FAST><<<(unsigned)blocks, threads, 0, st>>>(
-        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, L, nseg, nseg, T, nitems);
+        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, ld, L, nseg, nseg, T, nitems);
     BVG_LAUNCHED();
     return BVG_OK;
   }
@@ -382,7 +383,7 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
     const int64_t blocks = main_blocks + ceil_div(nitems_edge, kPackedThreads);
     if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
     act1d_cl_packed_kernel<Tin, Tout, FAST><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
-        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
+        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, ld, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
         nseg, nseg_head, tail_start, nitems_edge);
     BVG_LAUNCHED();
     return BVG_OK;
@@ -390,7 +391,7 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
   const int64_t blocks = ceil_div(nitems_edge, threads);
   if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
   act1d_cl_kernel<Tin, Tout, 2, FAST><<<(unsigned)blocks, threads, 0, st>>>(
-      (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, kEdge, nseg, nseg_head, T, nitems_edge);
+      (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, ld, kEdge, nseg, nseg_head, T, nitems_edge);
   BVG_LAUNCHED();
   return BVG_OK;
 }
@@ -398,21 +399,23 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
 // host entry used by the C ABI and by the vocoder plan
 int act1d_cl_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log,
                     const Taps& taps, int B, int64_t T, int C, int in_dtype, int out_dtype, bool fast,
-                    cudaStream_t st) {
+                    cudaStream_t st, int ld) {
   if (B <= 0 || T <= 0 || C <= 0) return BVG_OK;
+  if (ld <= 0) ld = C;
+  if (ld < C) BVG_FAIL(BVG_EINVAL, "act1d_cl: row pitch %d < channels %d", ld, C);
   typedef __nv_bfloat16 bf;
   if (in_dtype == BVG_F32 && out_dtype == BVG_F32)
-    return fast ? launch_cl<float, float, true>(dst, src, alpha_log, beta_log, taps, B, T, C, st)
-                : launch_cl<float, float, false>(dst, src, alpha_log, beta_log, taps, B, T, C, st);
+    return fast ? launch_cl<float, float, true>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st)
+                : launch_cl<float, float, false>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st);
   if (in_dtype == BVG_F32 && out_dtype == BVG_BF16)
-    return fast ? launch_cl<float, bf, true>(dst, src, alpha_log, beta_log, taps, B, T, C, st)
-                : launch_cl<float, bf, false>(dst, src, alpha_log, beta_log, taps, B, T, C, st);
+    return fast ? launch_cl<float, bf, true>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st)
+                : launch_cl<float, bf, false>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st);
   if (in_dtype == BVG_BF16 && out_dtype == BVG_BF16)
-    return fast ? launch_cl<bf, bf, true>(dst, src, alpha_log, beta_log, taps, B, T, C, st)
-                : launch_cl<bf, bf, false>(dst, src, alpha_log, beta_log, taps, B, T, C, st);
+    return fast ? launch_cl<bf, bf, true>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st)
+                : launch_cl<bf, bf, false>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st);
   if (in_dtype == BVG_BF16 && out_dtype == BVG_F32)
-    return fast ? launch_cl<bf, float, true>(dst, src, alpha_log, beta_log, taps, B, T, C, st)
-                : launch_cl<bf, float, false>(dst, src, alpha_log, beta_log, taps, B, T, C, st);
+    return fast ? launch_cl<bf, float, true>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st)
+                : launch_cl<bf, float, false>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st);
   BVG_FAIL(BVG_EDTYPE, "act1d_cl: unsupported dtype pair (%d -> %d)", in_dtype, out_dtype);
 }
 

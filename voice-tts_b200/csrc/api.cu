@@ -128,7 +128,8 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
   if (rc) return rc;
   const int dt = mode == BVG_MODE_BF16 ? BVG_BF16 : BVG_F32;
   const size_t es = dtype_size(dt);
-  const int Cin_p = pad_channels(Cin), Cout_p = pad_channels(Cout);
+  const int gran = 16;   // see vocoder_create
+  const int Cin_p = pad_channels(Cin, gran), Cout_p = pad_channels(Cout, gran);
   const int kk = up > 0 ? 3 : k;
   const int Cout_n = up > 0 ? up * Cout_p : Cout_p;
   const int Cout_r = round_up(Cout_n, 128);

@@ -33,8 +33,9 @@ bool conv_umma_supported(const ConvArgs& a);
 bool conv_act_fused_supported(const ConvArgs& a);
 int conv_act_fused_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps, cudaStream_t st);
 
+// C channels per row are processed; ld (0 = C) is the row pitch in elements
 int act1d_cl_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,
-                    int B, int64_t T, int C, int in_dtype, int out_dtype, bool fast, cudaStream_t st);
+                    int B, int64_t T, int C, int in_dtype, int out_dtype, bool fast, cudaStream_t st, int ld = 0);
 int act1d_bct_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,
                      int B, int C, int64_t T, int dtype, bool fast, cudaStream_t st);
 
@@ -49,7 +50,9 @@ int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, cons
                      int Cp, int64_t T, int use_tanh, cudaStream_t st);
 int f32_to_i16(int16_t* dst, const float* src, int64_t n, cudaStream_t st);
 
-static inline int pad_channels(int c) { return c < 16 ? 16 : round_up(c, 16); }
+// channel padding of the channels-last tensors (the tcgen05 kernels accept multiples of 8 - the zero fill of their
+// 64-channel TMA boxes completes the last K step - but 16 keeps every bf16 row a multiple of 32 bytes)
+static inline int pad_channels(int c, int gran = 16) { return c < 16 ? 16 : round_up(c, gran); }
 static inline size_t dtype_size(int dt) { return dt == BVG_BF16 ? 2 : 4; }
 
 }  // namespace bvg

@@ -39,12 +39,12 @@ conv_simt_kernel(ConvArgs a) {
     const bool wrow_ok = wrow < a.Cout_r;
     for (int ci0 = 0; ci0 < a.Cin_p; ci0 += TS_K) {
       float xv[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (trow_ok) {
+      if (trow_ok && ci0 + lq < a.Cin_p) {
         const Tin* p = in + tsrc * a.Cin_p + ci0 + lq;
 #pragma unroll
         for (int q = 0; q < 4; ++q) xv[q] = ld_mut_f32<Tin>(p + q);
       }
-      if (wrow_ok) {
+      if (wrow_ok && ci0 + lq < a.Cin_p) {
         const Tw* p = w + ((int64_t)j * a.Cout_r + wrow) * a.Cin_p + ci0 + lq;
 #pragma unroll
         for (int q = 0; q < 4; ++q) wv[q] = to_f32<Tw>(p[q]);
@@ -102,7 +102,7 @@ static int launch_simt(const ConvArgs& a, cudaStream_t st) {
 
 int conv_simt_launch(const ConvArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.T <= 0) return BVG_OK;
-  if (a.Cin_p % TS_K != 0) BVG_FAIL(BVG_EINVAL, "conv_simt: Cin_p=%d not a multiple of 16", a.Cin_p);
+  if (a.Cin_p % 4 != 0) BVG_FAIL(BVG_EINVAL, "conv_simt: Cin_p=%d not a multiple of 4", a.Cin_p);
   typedef __nv_bfloat16 bf;
   if (a.in_dtype == BVG_F32 && a.w_dtype == BVG_F32) return launch_simt<float, float>(a, st);
   if (a.in_dtype == BVG_BF16 && a.w_dtype == BVG_BF16) return launch_simt<bf, bf>(a, st);

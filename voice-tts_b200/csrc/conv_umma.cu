@@ -402,7 +402,7 @@ int umma_sm_count() {
   return n;
 }
 
-bool conv_umma_supported(const ConvArgs& a) {
+static bool conv_umma1_supported(const ConvArgs& a) {
   if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16) return false;
   if (a.Cin_p % 16 != 0 || a.Cout_r % UM_M != 0) return false;
   if (a.T <= 0 || a.T > 0x7fffffffLL / 2) return false;
@@ -411,10 +411,12 @@ bool conv_umma_supported(const ConvArgs& a) {
   return true;
 }
 
+bool conv_umma_supported(const ConvArgs& a) { return conv_umma2_supported(a) || conv_umma1_supported(a); }
+
 int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   if (a.B <= 0 || a.T <= 0) return BVG_OK;
-  if (!conv_umma_supported(a)) BVG_FAIL(BVG_EINVAL, "conv_umma: unsupported layer shape/dtype");
   if (!(variant & 8) && conv_umma2_supported(a)) return conv_umma2_launch(a, variant, st);   // v2 kernel (default)
+  if (!conv_umma1_supported(a)) BVG_FAIL(BVG_EINVAL, "conv_umma: unsupported layer shape/dtype");
   if (a.Cout_n <= 128 && !(variant & 4) && conv_umma_t_fits(a)) return conv_umma_t_launch(a, variant, st);   // time-major variant
   UmmaParams p;
   p.bias = a.bias; p.out = a.out; p.res = a.res; p.accum = a.accum; p.scale = a.scale;

@@ -402,7 +402,7 @@ static bool u2_plan(const ConvArgs& a, U2Params& p) {
   const int nin = u2_nin(a);
   if (nin < 0) return false;
   if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16) return false;
-  if (a.Cin_p % 16 != 0 || a.Cout_r % 128 != 0 || a.Cout_n <= 0) return false;
+  if (a.Cin_p % 8 != 0 || a.Cout_r % 128 != 0 || a.Cout_n <= 0) return false;
   if (a.T <= 0 || a.T > 0x3fffffffLL || a.B <= 0) return false;
   const int halo = (a.k - 1) * a.dil;
   if (halo > 64) return false;

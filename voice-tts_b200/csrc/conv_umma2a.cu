@@ -447,7 +447,7 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 static bool ua_plan(const ConvArgs& a, UAParams& p) {
   if (a.res || a.accum || a.scale != 1.f) return false;
   if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16 || a.out_dtype != BVG_BF16) return false;
-  if (a.Cin_p % 16 != 0 || a.Cout_r % 128 != 0 || a.Cout_n <= 0 || a.Cout_n % 8 != 0) return false;
+  if (a.Cin_p % 8 != 0 || a.Cout_r % 128 != 0 || a.Cout_n <= 0 || a.Cout_n % 8 != 0) return false;
   if (a.T <= 0 || a.T > 0x3fffffffLL || a.B <= 0) return false;
   const int halo = (a.k - 1) * a.dil;
   const int ncot = (int)ceil_div(a.Cout_n, 128);

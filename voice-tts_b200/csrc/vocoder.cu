@@ -93,10 +93,10 @@ static int dev_alloc(void** p, size_t bytes) {
   return BVG_OK;
 }
 
-static void init_conv(ConvW& c, int Cin, int Cout, int k, int dil, int up) {
+static void init_conv(ConvW& c, int Cin, int Cout, int k, int dil, int up, int gran) {
   c.Cin = Cin; c.Cout = Cout; c.k_torch = k; c.dil = dil; c.up = up;
-  c.Cin_p = pad_channels(Cin);
-  c.Cout_p = pad_channels(Cout);
+  c.Cin_p = pad_channels(Cin, gran);
+  c.Cout_p = pad_channels(Cout, gran);
   if (up > 0) {
     c.k = 3; c.dil = 1;
     c.Cout_n = up * c.Cout_p;
@@ -116,8 +116,8 @@ static int alloc_conv(ConvW& c, int w_dt) {
   return BVG_OK;
 }
 
-static int alloc_act(ActW& a, int C) {
-  a.C = C; a.Cp = pad_channels(C);
+static int alloc_act(ActW& a, int C, int gran) {
+  a.C = C; a.Cp = pad_channels(C, gran);
   int rc = dev_alloc((void**)&a.alpha, a.Cp * sizeof(float));
   if (rc) return rc;
   rc = dev_alloc((void**)&a.beta, a.Cp * sizeof(float));
@@ -269,7 +269,10 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   // algorithmic bytes: one read + one write of the unpadded tensor
   ProfScope ps(v, st, CAT_ACT, (double)B * T * a.C * (dtype_size(in_dt) + dtype_size(out_dt)));
   ps.cin = a.C; ps.cout = a.C; ps.k = (int)dtype_size(in_dt); ps.dil = (int)dtype_size(out_dt); ps.rows = (long long)B * T;
-  return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, a.Cp, in_dt, out_dt, fast, st);
+  // all Cp channels are processed: pad channels (alpha = beta = 0, input 0) come out as exact zeros, which the zero
+  // weight columns of the next conv need (a stale NaN bit pattern times 0 would poison the accumulator).  Skipping them
+  // (C real channels, row pitch Cp) was measured: 0.3 ms per step at the 24-channel stage - not worth a zero-fill pass.
+  return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, a.Cp, in_dt, out_dt, fast, st, a.Cp);
 }
 
 // ---- debug: order-independent checksums of intermediate tensors (BVG_DBG_SUMS=1), printed per forward ----
@@ -651,19 +654,22 @@ int vocoder_create(const bvg_config* cfg, bvg_vocoder** out) {
   v->cfg = *cfg;
   v->nst = cfg->num_upsamples; v->nk = cfg->num_kernels; v->nd = cfg->num_dilations;
   v->act_dt = cfg->mode == BVG_MODE_BF16 ? BVG_BF16 : BVG_F32;
-  v->mel_p = pad_channels(cfg->num_mels);
+  // channel padding granularity (conv.cuh: pad_channels).  8 is legal on the tcgen05 path, but 48-byte rows (24 channels)
+  // halve the TMA load rate of the last stage (measured: its convs 1.7-2.3x slower), so rows stay multiples of 32 bytes
+  const int gran = 16;
+  v->mel_p = pad_channels(cfg->num_mels, gran);
   v->C.resize(v->nst + 1); v->Cp.resize(v->nst + 1);
   v->C[0] = cfg->upsample_initial_channel;
   for (int i = 0; i < v->nst; ++i) { v->C[i + 1] = cfg->upsample_initial_channel >> (i + 1); v->total_up *= cfg->upsample_rates[i]; }
-  for (int i = 0; i <= v->nst; ++i) v->Cp[i] = pad_channels(v->C[i]);
+  for (int i = 0; i <= v->nst; ++i) v->Cp[i] = pad_channels(v->C[i], gran);
   for (int i = 0; i < 12; ++i) { v->act_post.taps.up[i] = 0.f; v->act_post.taps.down[i] = 0.f; }
 
 #define TRY(x) do { rc = (x); if (rc) { bvg_destroy(v); return rc; } } while (0)
-  init_conv(v->conv_pre, cfg->num_mels, v->C[0], 7, 1, 0);
+  init_conv(v->conv_pre, cfg->num_mels, v->C[0], 7, 1, 0, gran);
   TRY(alloc_conv(v->conv_pre, v->act_dt));
   v->ups.resize(v->nst);
   for (int i = 0; i < v->nst; ++i) {
-    init_conv(v->ups[i], v->C[i], v->C[i + 1], cfg->upsample_kernel_sizes[i], 1, cfg->upsample_rates[i]);
+    init_conv(v->ups[i], v->C[i], v->C[i + 1], cfg->upsample_kernel_sizes[i], 1, cfg->upsample_rates[i], gran);
     TRY(alloc_conv(v->ups[i], v->act_dt));
   }
   v->convs1.resize(v->nst * v->nk * v->nd); v->convs2.resize(v->nst * v->nk * v->nd);
@@ -672,13 +678,13 @@ int vocoder_create(const bvg_config* cfg, bvg_vocoder** out) {
     for (int j = 0; j < v->nk; ++j)
       for (int l = 0; l < v->nd; ++l) {
         const int ci = (i * v->nk + j) * v->nd + l;
-        init_conv(v->convs1[ci], v->C[i + 1], v->C[i + 1], cfg->resblock_kernel_sizes[j], cfg->resblock_dilations[j][l], 0);
-        init_conv(v->convs2[ci], v->C[i + 1], v->C[i + 1], cfg->resblock_kernel_sizes[j], 1, 0);
+        init_conv(v->convs1[ci], v->C[i + 1], v->C[i + 1], cfg->resblock_kernel_sizes[j], cfg->resblock_dilations[j][l], 0, gran);
+        init_conv(v->convs2[ci], v->C[i + 1], v->C[i + 1], cfg->resblock_kernel_sizes[j], 1, 0, gran);
         TRY(alloc_conv(v->convs1[ci], v->act_dt));
         TRY(alloc_conv(v->convs2[ci], v->act_dt));
-        for (int a = 0; a < 2; ++a) TRY(alloc_act(v->acts[(i * v->nk + j) * 2 * v->nd + 2 * l + a], v->C[i + 1]));
+        for (int a = 0; a < 2; ++a) TRY(alloc_act(v->acts[(i * v->nk + j) * 2 * v->nd + 2 * l + a], v->C[i + 1], gran));
       }
-  TRY(alloc_act(v->act_post, v->C[v->nst]));
+  TRY(alloc_act(v->act_post, v->C[v->nst], gran));
   TRY(dev_alloc((void**)&v->post_w, 7 * v->Cp[v->nst] * sizeof(float)));
 #undef TRY
   *out = v;
