@@ -117,6 +117,15 @@ int bvg_conv1d_res_fwd(float* dst, const float* src, const float* weight, const 
 int bvg_conv1d_act_fwd(float* dst, const float* src, const float* weight, const float* bias, const float* alpha_log,
                        const float* beta_log, const float* up_taps, const float* down_taps, int B, int Cin, int Cout,
                        int64_t T, int k, int dilation, int mode, bvg_stream_t stream);
+/* Second conv of an AMP unit with its residual AND the first activation of the next unit
+ * (bigvgan.py:138-139 `xt = c2(xt); x = xt + x`, then :134 `xt = a1(x)` of the next loop iteration):
+ *   dst_y   = conv1d(src) + bias + res                 (fp32 residual stream, [B, Cout, T])
+ *   dst_act = Activation1d_{alpha,beta}(dst_y)         (rounded to bf16 in BVG_MODE_BF16)
+ * One tcgen05 kernel in BVG_MODE_BF16; conv + activation kernels in BVG_MODE_FP32. */
+int bvg_conv1d_res_act_fwd(float* dst_act, float* dst_y, const float* src, const float* weight, const float* bias,
+                           const float* res, const float* alpha_log, const float* beta_log, const float* up_taps,
+                           const float* down_taps, int B, int Cin, int Cout, int64_t T, int k, int dilation, int mode,
+                           bvg_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Whole generator.  Build: bvg_create -> bvg_set_tensor for every state-dict

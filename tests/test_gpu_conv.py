@@ -193,3 +193,50 @@ def test_conv1d_fused_activation_batch_independence(ops):
     for i in range(B):
         yi = ops.conv1d_act(x[i:i + 1].contiguous().to(DEV), w.to(DEV), b.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "bf16", 0)
         assert torch.equal(yi, y[i:i + 1])
+
+
+RES_ACT_CASES = [  # B, Cin, Cout, T, k, dil
+    (1, 192, 192, 530, 7, 1), (2, 384, 384, 300, 3, 1), (1, 768, 768, 250, 3, 1), (1, 24, 24, 700, 3, 1), (2, 48, 48, 481, 11, 1),
+    (1, 96, 96, 1, 3, 1), (1, 64, 64, 5, 7, 1), (1, 128, 128, 239, 3, 1), (1, 32, 80, 257, 3, 1), (3, 16, 16, 33, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", RES_ACT_CASES, ids=[str(c) for c in RES_ACT_CASES])
+def test_conv1d_fused_residual_activation(ops, case):
+    """y = conv1d(x) + bias + res and Activation1d(y) from ONE tcgen05 kernel (bigvgan.py:134-139) against the fp64 oracle."""
+    B, Cin, Cout, T, k, d = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = bf(torch.randn(B, Cin, T, generator=g))
+    w = bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(B, Cout, T, generator=g)
+    al = torch.randn(Cout, generator=g) * 0.5
+    be = torch.randn(Cout, generator=g) * 0.5
+    taps = O.kaiser_taps(); tl = taps.tolist()
+    yref = O.conv1d(x.double(), w.double(), b.double(), d) + res.double()
+    aref = O.activation1d(yref, al.double(), be.double(), taps.double(), taps.double())
+    ya, y = ops.conv1d_res_act(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "bf16", 0)
+    ya, y = ya.cpu().double(), y.cpu().double()
+    assert (y - yref).abs().max() <= 1e-5 * float(yref.abs().max())
+    assert (ya - aref).abs().max() <= 2.0 ** -8 * float(aref.abs().max())
+    assert torch.equal(ya.float(), bf(ya.float()))
+    # y is bit-identical to what the plain residual kernel writes, the activation agrees with the two-kernel composition
+    y_plain = ops.conv1d_res(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), torch.empty(0, device=DEV), 1.0, False, d, "bf16", 0)
+    assert torch.equal(y_plain.cpu().double(), y)
+    ya2, y2 = ops.conv1d_res_act(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "bf16", 16)
+    assert torch.equal(y2.cpu().double(), y)
+    assert (ya2.cpu().double() - aref).abs().max() <= 2.0 ** -8 * float(aref.abs().max())
+
+
+def test_conv1d_fused_residual_activation_fp32_mode(ops):
+    g = torch.Generator().manual_seed(15)
+    B, C, T, k, d = 2, 24, 300, 7, 1
+    x = torch.randn(B, C, T, generator=g); w = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b = torch.randn(C, generator=g); res = torch.randn(B, C, T, generator=g)
+    al = torch.randn(C, generator=g) * 0.5; be = torch.randn(C, generator=g) * 0.5
+    taps = O.kaiser_taps(); tl = taps.tolist()
+    yref = O.conv1d(x.double(), w.double(), b.double(), d) + res.double()
+    aref = O.activation1d(yref, al.double(), be.double(), taps.double(), taps.double())
+    ya, y = ops.conv1d_res_act(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "fp32", 0)
+    assert (y.cpu().double() - yref).abs().max() <= 1e-5 * float(yref.abs().max())
+    assert (ya.cpu().double() - aref).abs().max() <= 1e-5 * float(aref.abs().max())

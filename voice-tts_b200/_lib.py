@@ -41,6 +41,7 @@ SYMBOLS = {
     "bvg_conv1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_conv1d_res_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_conv1d_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
+    "bvg_conv1d_res_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_convtr1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_create": (_i, [ctypes.POINTER(BvgConfig), ctypes.POINTER(_vp)]),
     "bvg_destroy": (None, [_vp]),

@@ -115,7 +115,8 @@ int bvg_act1d_cl_fwd(void* dst, const void* src, const float* alpha_log, const f
 static int dense_layer(float* dst, const float* src, const float* weight, const float* bias, int B, int Cin, int Cout,
                        int64_t T, int k, int dil, int up, int mode, cudaStream_t st, const float* res = nullptr,
                        const float* accum = nullptr, float scale = 1.f, int out_bf16 = 0,
-                       const float* act_alpha = nullptr, const float* act_beta = nullptr, const Taps* act_taps = nullptr) {
+                       const float* act_alpha = nullptr, const float* act_beta = nullptr, const Taps* act_taps = nullptr,
+                       float* dst_y = nullptr) {
   if (B < 0 || Cin <= 0 || Cout <= 0 || T < 0 || k <= 0) BVG_FAIL(BVG_EINVAL, "dense layer: bad dimension");
   const int variant = (mode >> 8) & 0xff;  // debug variants ride in the upper bits of `mode`
   mode &= 0xff;
@@ -137,7 +138,8 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
   void *xin = nullptr, *wp = nullptr;
   float *bp = nullptr, *yout = nullptr, *resp = nullptr, *accp = nullptr;
   if ((res || accum || out_bf16 || act_taps) && up > 0) BVG_FAIL(BVG_EINVAL, "fused residual / activation forms are defined for conv1d only");
-  if (act_taps && (res || accum)) BVG_FAIL(BVG_EINVAL, "fused activation form takes no residual");
+  if (act_taps && (accum || scale != 1.f)) BVG_FAIL(BVG_EINVAL, "fused activation form takes no accumulate operand / scale");
+  if (act_taps && ((res != nullptr) != (dst_y != nullptr))) BVG_FAIL(BVG_EINVAL, "fused activation form: residual and y output go together");
   const size_t b_in = (size_t)B * T * Cin_p * es, b_w = (size_t)kk * Cout_r * Cin_p * es, b_b = (size_t)Cout_r * 4,
                b_out = (size_t)B * T * Cout_n * 4;
   unsigned char* blk = nullptr;
@@ -179,21 +181,26 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
     ca.B = B; ca.T = T; ca.Cin_p = Cin_p; ca.Cout_n = Cout_n; ca.Cout_r = Cout_r; ca.out_ld = Cout_n;
     ca.k = kk; ca.dil = up > 0 ? 1 : dil;
     if (act_taps) {
-      // conv + bias, then Activation1d: one kernel in bf16 mode (result rounded to bf16), two kernels otherwise
+      // conv + bias (+ residual), then Activation1d: one kernel in bf16 mode (result rounded to bf16), two kernels otherwise
       ca.out_dtype = dt;
       if (dt == BVG_BF16 && !(variant & 16) && conv_act_fused_supported(ca)) {
-        rc = conv_act_fused_launch(ca, alp, bep, *act_taps, st);
+        rc = conv_act_fused_launch(ca, alp, bep, *act_taps, st, res ? accp : nullptr);   // accp: y = conv + bias + res
         if (rc) break;
         rc = btc_to_bct(dst, yout, BVG_BF16, B, Cout, Cout_p, Tout, st);
+        if (!rc && res) rc = btc_to_bct(dst_y, accp, BVG_F32, B, Cout, Cout_p, Tout, st);
         break;
       }
-      ca.out = resp;   // intermediate conv result (operand dtype)
+      // intermediate conv result: operand dtype without residual, the fp32 residual stream with it
+      ca.out = accp;
+      const int mid_dt = res ? BVG_F32 : dt;
+      ca.out_dtype = mid_dt;
       if (dt == BVG_BF16 && conv_umma_supported(ca)) rc = conv_umma_launch(ca, variant, st);
       else rc = conv_simt_launch(ca, st);
       if (rc) break;
-      rc = act1d_cl_launch(yout, resp, alp, bep, *act_taps, B, T, Cout_n, dt, dt, dt == BVG_BF16, st);
+      rc = act1d_cl_launch(yout, accp, alp, bep, *act_taps, B, T, Cout_n, mid_dt, dt, dt == BVG_BF16, st);
       if (rc) break;
       rc = btc_to_bct(dst, yout, dt, B, Cout, Cout_p, Tout, st);
+      if (!rc && res) rc = btc_to_bct(dst_y, accp, BVG_F32, B, Cout, Cout_p, Tout, st);
       break;
     }
     if (dt == BVG_BF16 && conv_umma_supported(ca)) rc = conv_umma_launch(ca, variant, st);
@@ -233,6 +240,20 @@ int bvg_conv1d_act_fwd(float* dst, const float* src, const float* weight, const 
   host_taps(&taps, up_taps, down_taps);
   return dense_layer(dst, src, weight, bias, B, Cin, Cout, T, k, dilation, 0, mode, (cudaStream_t)stream, nullptr, nullptr,
                      1.f, 0, alpha_log, beta_log, &taps);
+}
+
+int bvg_conv1d_res_act_fwd(float* dst_act, float* dst_y, const float* src, const float* weight, const float* bias,
+                           const float* res, const float* alpha_log, const float* beta_log, const float* up_taps,
+                           const float* down_taps, int B, int Cin, int Cout, int64_t T, int k, int dilation, int mode,
+                           bvg_stream_t stream) {
+  const int m = mode & 0xff;
+  if (m != BVG_MODE_FP32 && m != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_conv1d_res_act_fwd: unknown mode %d", mode);
+  if (!dst_y || !res || !alpha_log || !beta_log || !up_taps || !down_taps)
+    BVG_FAIL(BVG_EINVAL, "bvg_conv1d_res_act_fwd: null pointer");
+  Taps taps;
+  host_taps(&taps, up_taps, down_taps);
+  return dense_layer(dst_act, src, weight, bias, B, Cin, Cout, T, k, dilation, 0, mode, (cudaStream_t)stream, res, nullptr,
+                     1.f, 0, alpha_log, beta_log, &taps, dst_y);
 }
 
 int bvg_convtr1d_fwd(float* dst, const float* src, const float* weight, const float* bias, int B, int Cin, int Cout,

@@ -31,7 +31,9 @@ int conv_umma_launch(const ConvArgs& a, int variant, cudaStream_t st);
 bool conv_umma_supported(const ConvArgs& a);
 // Conv1d + bias followed by Activation1d (alpha/beta log-scale per output channel), bf16 result, one kernel
 bool conv_act_fused_supported(const ConvArgs& a);
-int conv_act_fused_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps, cudaStream_t st);
+// with a.res: out = bf16(act(conv + bias + res)), y_out = conv + bias + res (fp32 residual stream; must not alias a.res)
+int conv_act_fused_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps, cudaStream_t st,
+                          float* y_out = nullptr);
 
 // C channels per row are processed; ld (0 = C) is the row pitch in elements
 int act1d_cl_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,

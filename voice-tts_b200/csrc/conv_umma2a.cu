@@ -52,6 +52,9 @@ struct UAParams {
   const float* bias;
   const float* alpha_log;   // [Cout] log-scale snake parameters of the fused activation
   const float* beta_log;
+  const float* res;         // RES mode: fp32 residual [B, T, out_ld] ...
+  float* y;                 // ... and the fp32 sum (conv + bias + res) written for the next unit's residual
+  int out_ld;
   TapsPacked tp;
   int B, T;
   int Cin_p, nchunks;
@@ -101,11 +104,23 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 // Step i of a sub-segment (t = t_first - 6 + i) takes x[t+5] into the window and produces v[2t+5], v[2t+6]
 // and (i >= 6) y[t].  EDGE: the segment touches a sequence end (x / v replicate rules, as the generic path of
 // act1d_cl_kernel); handled per half on unpacked values.
-template <bool EDGE>
+// RES: x = accumulator + bias + res[t][channel] (the AMPBlock1 residual, bigvgan.py:139); x is also stored as the fp32
+// residual stream y[t][channel] for the rows this sub-segment owns.  rrow / yrow point at column 0 of sub-segment A
+// (time tseg - 6) / at its first owned row (time tseg) for this lane's channel; rows are p.out_ld elements apart.
+template <bool EDGE, bool RES>
 __device__ __forceinline__ void ua_segment(const UAParams& p, uint32_t taddr, int tseg, float bv, float a, float ib,
                                            uint32_t stg, int wbox, int lane, bool lane_ok, const void* omap,
-                                           int ch0, int b, uint32_t& nstore) {
+                                           int ch0, int b, uint32_t& nstore, const float* __restrict__ rrow,
+                                           float* __restrict__ yrow) {
   const int L = p.S >> 1, Rs = p.Rs, T = p.T, Tlast = p.T - 1;
+  const int64_t ld = p.out_ld;
+  // residual row of column c (time tseg - 6 + c); sequence ends: any in-range row will do, the value is overridden
+  auto rload = [&](int c) -> float {
+    if (!RES) return 0.f;
+    int t = tseg - 6 + c;
+    if (EDGE) t = t < 0 ? 0 : (t > Tlast ? Tlast : t);
+    return lane_ok ? BVG_LDG(rrow + (int64_t)(t - (tseg - 6)) * ld) : 0.f;
+  };
   const int bodies_per_round = Rs / 6;
   const uint32_t half_bytes = UA_STAGE_BYTES / 2;            // A rows, then (128-byte aligned for the TMA) B rows
   const float hbf = 0.5f * ib;
@@ -121,10 +136,21 @@ __device__ __forceinline__ void ua_segment(const UAParams& p, uint32_t taddr, in
   tmem_ld_32x2(taddr + 9, nA[4], nA[5]);
   tmem_ld_32x4(taddr + L + 5, nB[0], nB[1], nB[2], nB[3]);
   tmem_ld_32x2(taddr + L + 9, nB[4], nB[5]);
-  tmem_ld_wait5(preA);
-  tmem_ld_wait5(preB);
+  float rA[6], rB[6];                           // residual of the current body; slot s is refilled for the next body once used
+  {
+    float qA[5], qB[5];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) X[i] = add2(pk2(__uint_as_float(preA[i]), __uint_as_float(preB[i])), bv2);
+    for (int i = 0; i < 5; ++i) { qA[i] = rload(i); qB[i] = rload(L + i); }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { rA[i] = rload(5 + i); rB[i] = rload(L + 5 + i); }
+    tmem_ld_wait5(preA);
+    tmem_ld_wait5(preB);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      X[i] = add2(pk2(__uint_as_float(preA[i]), __uint_as_float(preB[i])), bv2);
+      if (RES) X[i] = add2(X[i], pk2(qA[i], qB[i]));
+    }
+  }
   X[5] = pk2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 12; ++i) V[i] = pk2(0.f, 0.f);
@@ -159,16 +185,29 @@ __device__ __forceinline__ void ua_segment(const UAParams& p, uint32_t taddr, in
     const bool left = EDGE && j == 0 && tseg == 0;
     if (left) {
       // sub-segment A starts the sequence: x[t < 0] := x[0]; x[0] is the second column of this body
-      const float x0 = __uint_as_float(cA[1]) + bv;
+      const float x0 = __uint_as_float(cA[1]) + bv + (RES ? rA[1] : 0.f);
 #pragma unroll
       for (int i = 0; i < 5; ++i) { float lo, hi; upk2(X[i], lo, hi); X[i] = pk2(x0, hi); }
       cA[0] = cA[1];
+      if (RES) rA[0] = rA[1];
       xlastA = x0;
     }
     const int tb = tseg - 6 + 6 * j;           // t of step 0 of this body in sub-segment A (B: + L)
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       f32x2 xin = add2(pk2(__uint_as_float(cA[s]), __uint_as_float(cB[s])), bv2);
+      if (RES) {
+        xin = add2(xin, pk2(rA[s], rB[s]));
+        if (j + 1 < nbody) { rA[s] = rload(11 + 6 * j + s); rB[s] = rload(L + 11 + 6 * j + s); }
+        // this column is time tseg + o (A) / tseg + L + o (B); rows 0 <= o < L are the ones the sub-segment owns
+        const int o = 6 * j + s - 1;
+        if (lane_ok && o >= 0 && o < L) {
+          float ya, yb;
+          upk2(xin, ya, yb);
+          if (!EDGE || tseg + o <= Tlast) yrow[(int64_t)o * ld] = ya;
+          if (!EDGE || tseg + L + o <= Tlast) yrow[(int64_t)(L + o) * ld] = yb;
+        }
+      }
       if (EDGE) {
         float xa, xb;
         upk2(xin, xa, xb);
@@ -254,6 +293,7 @@ __device__ __forceinline__ void ua_segment(const UAParams& p, uint32_t taddr, in
   }
 }
 
+template <bool RES>
 __global__ void __launch_bounds__(UA_THREADS, 1)
 conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out_tail,
@@ -423,10 +463,15 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       if (warp_ok && tseg < p.T) {
         const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * 256u + (uint32_t)(seg * p.S);
         const bool interior = tseg >= UA_LEAD && tseg + p.S + 5 <= p.T - 1;
+        const int64_t row0 = (int64_t)t.b * p.T + tseg;
+        const float* rrow = RES ? p.res + (row0 - 6) * p.out_ld + (t.cot * CW + ch) : nullptr;
+        float* yrow = RES ? p.y + row0 * p.out_ld + (t.cot * CW + ch) : nullptr;
         if (interior)
-          ua_segment<false>(p, taddr, tseg, bv, a, ib, stg, wbox, lane, lane_ok, omap, t.cot * CW + lane0, t.b, nstore);
+          ua_segment<false, RES>(p, taddr, tseg, bv, a, ib, stg, wbox, lane, lane_ok, omap, t.cot * CW + lane0, t.b, nstore,
+                                 rrow, yrow);
         else
-          ua_segment<true>(p, taddr, tseg, bv, a, ib, stg, wbox, lane, lane_ok, omap, t.cot * CW + lane0, t.b, nstore);
+          ua_segment<true, RES>(p, taddr, tseg, bv, a, ib, stg, wbox, lane, lane_ok, omap, t.cot * CW + lane0, t.b, nstore,
+                                rrow, yrow);
       }
       tmem_ld_wait();
       tc_fence_before();
@@ -445,7 +490,7 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
 // ------------------------------------------------------------------ host side ----
 static bool ua_plan(const ConvArgs& a, UAParams& p) {
-  if (a.res || a.accum || a.scale != 1.f) return false;
+  if (a.accum || a.scale != 1.f) return false;
   if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16 || a.out_dtype != BVG_BF16) return false;
   if (a.Cin_p % 8 != 0 || a.Cout_r % 128 != 0 || a.Cout_n <= 0 || a.Cout_n % 8 != 0) return false;
   if (a.T <= 0 || a.T > 0x3fffffffLL || a.B <= 0) return false;
@@ -458,6 +503,8 @@ static bool ua_plan(const ConvArgs& a, UAParams& p) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.out);
   if (al & 15) return false;
   p.bias = a.bias;
+  p.res = a.res; p.y = nullptr; p.out_ld = a.out_ld;
+  if (a.res && (reinterpret_cast<uintptr_t>(a.res) & 3)) return false;
   p.B = a.B; p.T = (int)a.T;
   p.Cin_p = a.Cin_p; p.nchunks = (int)ceil_div(a.Cin_p, 64);
   p.k = a.k; p.dil = a.dil; p.center = (a.k - 1) / 2;
@@ -488,11 +535,15 @@ bool conv_umma2a_supported(const ConvArgs& a) {
 }
 
 int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* y_out) {
   if (a.B <= 0 || a.T <= 0) return BVG_OK;
   UAParams p;
   if (!ua_plan(a, p)) BVG_FAIL(BVG_EINVAL, "conv_umma2a: unsupported layer shape/dtype");
   if (!alpha_log || !beta_log) BVG_FAIL(BVG_EINVAL, "conv_umma2a: null activation parameters");
+  if ((a.res != nullptr) != (y_out != nullptr)) BVG_FAIL(BVG_EINVAL, "conv_umma2a: residual and y output go together");
+  if (a.res && static_cast<const void*>(a.res) == static_cast<const void*>(y_out))
+    BVG_FAIL(BVG_EINVAL, "conv_umma2a: y must not alias the residual (tiles read each other's halo rows)");
+  p.y = y_out;
   p.alpha_log = alpha_log; p.beta_log = beta_log;
   make_taps_packed(&p.tp, taps);
   CUtensorMap mx, mw, mo, mt;
@@ -516,16 +567,21 @@ int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* b
   }
   const int sms = umma_sm_count();
   const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
-  BVG_CUDA(cudaFuncSetAttribute(conv_umma2a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES));
-  conv_umma2a_kernel<<<grid, UA_THREADS, UA_SMEM_BYTES, st>>>(mx, mw, mo, mt, p);
+  if (a.res) {
+    BVG_CUDA(cudaFuncSetAttribute(conv_umma2a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES));
+    conv_umma2a_kernel<true><<<grid, UA_THREADS, UA_SMEM_BYTES, st>>>(mx, mw, mo, mt, p);
+  } else {
+    BVG_CUDA(cudaFuncSetAttribute(conv_umma2a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES));
+    conv_umma2a_kernel<false><<<grid, UA_THREADS, UA_SMEM_BYTES, st>>>(mx, mw, mo, mt, p);
+  }
   BVG_LAUNCHED();
   return BVG_OK;
 }
 
 bool conv_act_fused_supported(const ConvArgs& a) { return conv_umma2a_supported(a); }
 int conv_act_fused_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps,
-                          cudaStream_t st) {
-  return conv_umma2a_launch(a, alpha_log, beta_log, taps, st);
+                          cudaStream_t st, float* y_out) {
+  return conv_umma2a_launch(a, alpha_log, beta_log, taps, st, y_out);
 }
 
 }  // namespace bvg

@@ -32,7 +32,9 @@ bool conv_umma2_supported(const ConvArgs& a);
 int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st);
 // v2 kernel with the following Activation1d fused into its epilogue (conv_umma2a.cu); bf16 output only
 bool conv_umma2a_supported(const ConvArgs& a);
-int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps, cudaStream_t st);
+// a.res != nullptr: out = act(conv + bias + res) and y_out = conv + bias + res (fp32, same layout; must not alias a.res)
+int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* beta_log, const Taps& taps, cudaStream_t st,
+                       float* y_out = nullptr);
 int conv_umma_t_launch(const ConvArgs& a, int variant, cudaStream_t st);
 bool conv_umma_t_fits(const ConvArgs& a);
 

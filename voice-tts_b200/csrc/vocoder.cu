@@ -61,7 +61,9 @@ struct bvg_vocoder {
   bool finalized = false;
   // options
   int opt_graph = 0, opt_conv_impl = 0, opt_umma_variant = 0, opt_fast_sin = -1;
+  int opt_fuse_res = 1;            // conv2 of an AMP unit adds the residual AND applies the next unit's first activation (bf16 mode)
   int opt_fuse_act = 1;            // conv1 of an AMP unit applies the following activation in its epilogue (bf16 mode)
+  int fuse_res_min_kc = 4096;      // smallest k * Cin whose conv2 takes the fused residual + activation epilogue
   int opt_streams = 1;             // AMP blocks of one stage run on up to this many streams (1 = serial; >1 experimental)
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // internal streams for AMP blocks 0 .. nk-2
   cudaEvent_t ev_fork = nullptr, ev_blk[3] = {nullptr, nullptr, nullptr};
@@ -130,7 +132,7 @@ static int alloc_act(ActW& a, int C, int gran) {
 // a1 / m / a2 / y exist once per concurrently running AMP block (nb sets)
 struct Buffers {
   void *mel, *p0, *nx, *a1[4], *m[4], *a2[4];
-  float *x, *y[4], *xs;
+  float *x, *y[4], *y2[4], *xs;   // y / y2: the residual stream of a block ping-pongs (fused conv2 reads halo rows of its input)
   int nb;
 };
 
@@ -160,12 +162,13 @@ static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
   const size_t o_x = take(nmax * 4);
   const size_t o_xs = take(nmax * 4);
   const int nb = n_block_streams(v);
-  size_t o_a1[4], o_m[4], o_a2[4], o_y[4];
+  size_t o_a1[4], o_m[4], o_a2[4], o_y[4], o_y2[4];
   for (int j = 0; j < nb; ++j) {
     o_a1[j] = take(nmax * es);
     o_m[j] = take(nmax * es);
     o_a2[j] = take(nmax * es);
     o_y[j] = take(nmax * 4);
+    o_y2[j] = take(nmax * 4);
   }
   if (out) {
     unsigned char* base = (unsigned char*)v->arena;
@@ -175,6 +178,7 @@ static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
     for (int j = 0; j < nb; ++j) {
       out->a1[j] = base + o_a1[j]; out->m[j] = base + o_m[j]; out->a2[j] = base + o_a2[j];
       out->y[j] = (float*)(base + o_y[j]);
+      out->y2[j] = (float*)(base + o_y2[j]);
     }
   }
   return off;
@@ -261,6 +265,34 @@ static int run_conv_act(bvg_vocoder* v, const ConvW& c, const ActW& act, const v
   ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   ps.cin = c.Cin; ps.cout = c.Cout; ps.k = c.k_torch; ps.dil = 100 + c.dil; ps.rows = (long long)B * T;
   return conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st);
+}
+
+// c2 + residual of unit l and a1 of unit l+1 (bigvgan.py:139 `x = xt + x`, then :134 of the next iteration) as ONE launch:
+// a_out = bf16(act(conv + bias + res)), y_out = conv + bias + res (fp32)
+static bool can_fuse_conv_res_act(const bvg_vocoder* v, const ConvW& c, const void* in, void* a_out, const float* res,
+                                  int B, int64_t T) {
+  if (!v->opt_fuse_res || v->cfg.mode != BVG_MODE_BF16 || v->opt_conv_impl == 1 || v->opt_fast_sin == 0) return false;
+  // measured on B200 (profiles/r01_layer_times_c.txt): the residual rows come straight from HBM/L2 into registers
+  // (one body = 6 steps ahead) and with two epilogue warps per scheduler that latency only hides under long MMA streams:
+  // 768 ch k >= 7 and 384 ch k = 11 gain 15-20 %, 384 ch k = 3 and everything narrower lose; fuse_res = 2 forces it
+  if (v->opt_fuse_res == 1 && c.k * c.Cin_p < v->fuse_res_min_kc) return false;
+  ConvArgs a;
+  a.in = in; a.w = c.w; a.bias = c.bias; a.out = a_out; a.res = res; a.accum = nullptr; a.scale = 1.f;
+  a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
+  a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
+  a.k = c.k; a.dil = c.dil;
+  return conv_act_fused_supported(a);
+}
+static int run_conv_res_act(bvg_vocoder* v, const ConvW& c, const ActW& act, const void* in, void* a_out, const float* res,
+                            float* y_out, int B, int64_t T, cudaStream_t st) {
+  ConvArgs a;
+  a.in = in; a.w = c.w; a.bias = c.bias; a.out = a_out; a.res = res; a.accum = nullptr; a.scale = 1.f;
+  a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
+  a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
+  a.k = c.k; a.dil = c.dil;
+  ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
+  ps.cin = c.Cin; ps.cout = c.Cout; ps.k = c.k_torch; ps.dil = 200 + c.dil; ps.rows = (long long)B * T;
+  return conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st, y_out);
 }
 
 static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, void* out, int out_dt, int B,
@@ -353,11 +385,15 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
       static const int dbg_serial = getenv("BVG_SERIAL_BLOCKS") ? atoi(getenv("BVG_SERIAL_BLOCKS")) : 0;   // debug: bit j = block j starts after block j-1
       if (((dbg_serial >> j) & 1) && nb > 1 && j > 0) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0));
       const float* cur = bf.x;
+      bool a1_ready = false;     // a1 of this unit already came out of the previous unit's fused conv2
       for (int l = 0; l < v->nd; ++l) {
         const int ci = (i * v->nk + j) * v->nd + l;
         const int ai = (i * v->nk + j) * 2 * v->nd + 2 * l;
-        rc = run_act(v, v->acts[ai], cur, BVG_F32, bf.a1[slot], adt, B, T, sj);
-        if (rc) return rc;
+        if (!a1_ready) {
+          rc = run_act(v, v->acts[ai], cur, BVG_F32, bf.a1[slot], adt, B, T, sj);
+          if (rc) return rc;
+        }
+        a1_ready = false;
         const size_t nel = (size_t)B * T * v->Cp[i + 1];
         g_dbg.add(bf.a1[slot], nel * dtype_size(adt), "a1", i, j, l, sj);
         if (can_fuse_conv_act(v, v->convs1[ci], bf.a1[slot], bf.a2[slot], B, T)) {
@@ -372,9 +408,15 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
         }
         g_dbg.add(bf.a2[slot], nel * dtype_size(adt), "a2", i, j, l, sj);
         if (l < v->nd - 1) {
-          rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, bf.y[slot], BVG_F32, cur, nullptr, 1.f, B, T, sj);
-          cur = bf.y[slot];
-          g_dbg.add(bf.y[slot], nel * 4, "y", i, j, l, sj);
+          float* ynext = (l & 1) ? bf.y2[slot] : bf.y[slot];
+          if (can_fuse_conv_res_act(v, v->convs2[ci], bf.a2[slot], bf.a1[slot], cur, B, T)) {
+            rc = run_conv_res_act(v, v->convs2[ci], v->acts[ai + 2], bf.a2[slot], bf.a1[slot], cur, ynext, B, T, sj);
+            a1_ready = true;
+          } else {
+            rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, ynext, BVG_F32, cur, nullptr, 1.f, B, T, sj);
+          }
+          cur = ynext;
+          g_dbg.add(ynext, nel * 4, "y", i, j, l, sj);
         } else {
           const bool to_next = (j == v->nk - 1) && !last_stage;
           if (nb > 1 && j > 0) { prof_break(v); BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0)); }   // XS of block j-1
@@ -795,6 +837,13 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
   else if (!strcmp(key, "fast_sin")) v->opt_fast_sin = value;
   else if (!strcmp(key, "workspace_mb")) v->opt_ws_cap_mb = value;
   else if (!strcmp(key, "profile")) v->opt_profile = value;
+  else if (!strcmp(key, "fuse_res") || !strcmp(key, "fuse_res_min_kc")) {
+    BVG_CUDA(cudaSetDevice(v->cfg.device));
+    BVG_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
+    v->graphs.clear();
+    if (!strcmp(key, "fuse_res")) v->opt_fuse_res = value; else v->fuse_res_min_kc = value;
+  }
   else if (!strcmp(key, "fuse_act")) {
     if (value != v->opt_fuse_act) {
       BVG_CUDA(cudaSetDevice(v->cfg.device));

@@ -184,6 +184,41 @@ def _(x, weight, bias, alpha_log, beta_log, up_taps, down_taps, dilation, precis
     return x.new_empty(x.shape[0], weight.shape[0], x.shape[2])
 
 
+@torch.library.custom_op("bvg_b200::conv1d_res_act", mutates_args=())
+def conv1d_res_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, res: torch.Tensor, alpha_log: torch.Tensor,
+                   beta_log: torch.Tensor, up_taps: List[float], down_taps: List[float], dilation: int, precision: str,
+                   variant: int) -> List[torch.Tensor]:
+    """[Activation1d(y), y] with y = conv1d(x) + bias + res: `xt = c2(xt); x = xt + x` and the next unit's `a1(x)`
+    (bigvgan.py:134-139) as one tcgen05 kernel in bf16 mode (variant 16 forces the two-kernel composition)."""
+    _require_cuda(x, "x")
+    B, Cin, T = x.shape
+    Cout, Cin2, k = weight.shape
+    if Cin2 != Cin or x.dtype != torch.float32 or tuple(res.shape) != (B, Cout, T):
+        raise RuntimeError("conv1d_res_act: expects fp32 x [B,Cin,T], weight [Cout,Cin,k], res [B,Cout,T]")
+    w = weight.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    a = alpha_log.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    b = beta_log.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    r = res.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    bptr = 0
+    if bias.numel():
+        bb = bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        bptr = bb.data_ptr()
+    ya = torch.empty(B, Cout, T, device=x.device, dtype=torch.float32)
+    y = torch.empty(B, Cout, T, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bvg_conv1d_res_act_fwd(ya.data_ptr(), y.data_ptr(), x.data_ptr(), w.data_ptr(), bptr, r.data_ptr(),
+                                                a.data_ptr(), b.data_ptr(), _lib.taps_array(up_taps),
+                                                _lib.taps_array(down_taps), B, Cin, Cout, T, k, dilation,
+                                                _mode(precision, variant), _stream(x))
+    _lib.check(rc, "bvg_conv1d_res_act_fwd")
+    return [ya, y]
+
+
+@conv1d_res_act.register_fake
+def _(x, weight, bias, res, alpha_log, beta_log, up_taps, down_taps, dilation, precision, variant):
+    return [x.new_empty(x.shape[0], weight.shape[0], x.shape[2]), x.new_empty(x.shape[0], weight.shape[0], x.shape[2])]
+
+
 @torch.library.custom_op("bvg_b200::conv_transpose1d", mutates_args=())
 def conv_transpose1d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, precision: str,
                      variant: int) -> torch.Tensor:
