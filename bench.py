@@ -188,24 +188,26 @@ def run_reference(args, rank, world):
 
 
 def act_sweep(dev, pk):
-    """BASELINE config 3: fused Activation1d HBM sweep on [B,C,T] (operator layout)."""
+    """BASELINE config 3: fused Activation1d HBM sweep on [B,C,T] (operator layout, bvg_act1d_fwd).
+    Algorithmic bytes = 2 * B*C*T * sizeof(dtype).  Three series: bf16 I/O (fast snake), fp32 I/O with the
+    accurate snake (the <= 1e-5 parity mode) and fp32 I/O with the fast snake (BVG_ACT_FAST_SIN)."""
     import torch
     ops = importlib.import_module("voice-tts_b200.ops")
     from oracle import bigvgan_oracle as O
     taps = O.kaiser_taps().tolist()
     rows = []
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    for dt in (torch.bfloat16, torch.float32):
+    for dt, fast in ((torch.bfloat16, True), (torch.float32, False), (torch.float32, True)):
         for C in (24, 48, 192, 768, 1536):
             for T in (8192, 131072, 2097152):
                 es = 2 if dt == torch.bfloat16 else 4
-                B = max(1, min(64, (256 << 20) // (C * T * es)))
+                # >= 256 MB per tensor where possible (2x the 126 MB L2), plus an explicit L2 flush between runs
+                B = max(1, -(-(256 << 20) // (C * T * es)))
                 if B * C * T * es > (3 << 30):
                     continue
                 x = torch.randn(B, C, T, device=dev).to(dt)
                 a = torch.randn(C, device=dev) * 0.5
                 b = torch.randn(C, device=dev) * 0.5
-                fast = dt == torch.bfloat16
                 for _ in range(2):
                     ops.act1d(x, a, b, taps, taps, fast)
                 ts = []
@@ -219,8 +221,8 @@ def act_sweep(dev, pk):
                     ts.append(e0.elapsed_time(e1))
                 ts.sort()
                 gbs = 2.0 * B * C * T * es / (ts[len(ts) // 2] * 1e-3) / 1e9
-                rows.append({"dtype": str(dt)[6:], "B": B, "C": C, "T": T, "ms": ts[len(ts) // 2], "GBps": round(gbs, 1),
-                             "frac_hbm": round(gbs / pk["hbm_gbs"], 3)})
+                rows.append({"dtype": str(dt)[6:], "snake": "fast" if fast else "accurate", "B": B, "C": C, "T": T,
+                             "ms": ts[len(ts) // 2], "GBps": round(gbs, 1), "frac_hbm": round(gbs / pk["hbm_gbs"], 3)})
                 del x
     return rows
 
