@@ -244,9 +244,10 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
 // c1 followed by a2 of one AMP unit (bigvgan.py:136-138) as ONE launch when the fused kernel takes the layer
 static bool can_fuse_conv_act(const bvg_vocoder* v, const ConvW& c, const void* in, void* out, int B, int64_t T) {
   if (!v->opt_fuse_act || v->cfg.mode != BVG_MODE_BF16 || v->opt_conv_impl == 1 || v->opt_fast_sin == 0) return false;
-  // measured on B200 (profiles/r01_layer_times_*.txt): for <= 64-channel k = 3 layers the epilogue activation (two
-  // warps per scheduler, idle replica lanes) costs more than the stand-alone kernel it replaces; opt_fuse_act = 2 forces it
-  if (v->opt_fuse_act == 1 && c.Cout_n <= 64 && c.k == 3) return false;
+  // measured on B200 (profiles/r01_layer_times_d.txt, fused vs conv + stand-alone activation): below 192 channels the
+  // epilogue activation (two warps per scheduler, a quarter of the TMEM lanes idle) only wins when the MMA stream is long
+  // (k = 11); opt_fuse_act = 2 forces the fusion everywhere
+  if (v->opt_fuse_act == 1 && c.Cout_n < 192 && c.k < 11) return false;
   ConvArgs a;
   a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = nullptr; a.accum = nullptr; a.scale = 1.f;
   a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
@@ -791,13 +792,21 @@ int vocoder_forward_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
     BVG_CUDA(cudaMalloc(&v->dev_wav, wav_bytes));
     v->pin_wav_bytes = wav_bytes;
   }
-  memcpy(v->pin_mel, mel_host, mel_bytes);
-  BVG_CUDA(cudaMemcpyAsync(v->dev_mel, v->pin_mel, mel_bytes, cudaMemcpyHostToDevice, st));
+  // page-locked caller buffers (cudaHostAlloc / cudaHostRegister, torch pin_memory) are DMA'd directly; pageable ones
+  // go through the handle's pinned staging buffers
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool mel_direct = is_pinned(mel_host), wav_direct = is_pinned(wav_host);
+  if (!mel_direct) memcpy(v->pin_mel, mel_host, mel_bytes);
+  BVG_CUDA(cudaMemcpyAsync(v->dev_mel, mel_direct ? mel_host : v->pin_mel, mel_bytes, cudaMemcpyHostToDevice, st));
   int rc = vocoder_forward(v, v->dev_mel, v->dev_wav, wav_dtype, B, T0, st);
   if (rc) return rc;
-  BVG_CUDA(cudaMemcpyAsync(v->pin_wav, v->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, st));
+  BVG_CUDA(cudaMemcpyAsync(wav_direct ? wav_host : v->pin_wav, v->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, st));
   BVG_CUDA(cudaStreamSynchronize(st));
-  memcpy(wav_host, v->pin_wav, wav_bytes);
+  if (!wav_direct) memcpy(wav_host, v->pin_wav, wav_bytes);
   return BVG_OK;
 }
 
