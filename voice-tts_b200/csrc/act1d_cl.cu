@@ -19,6 +19,15 @@
 
 namespace bvg {
 
+// 8 pad channels right behind a channel pair (row pitch = channels + 8): exact zeros, so that the zero weight columns of the
+// next conv never meet a stale NaN bit pattern.  Issued by the thread that owns the LAST real pair, at a constant offset.
+__device__ __forceinline__ void store_pad8(float* p) {
+  *reinterpret_cast<float4*>(p + 2) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(p + 6) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void store_pad8(__nv_bfloat16* p) { *reinterpret_cast<uint4*>(p + 2) = make_uint4(0u, 0u, 0u, 0u); }
+
+
 template <typename T, int VEC>
 struct VecIO;
 template <>
@@ -82,7 +91,7 @@ struct VecIO<__nv_bfloat16, 2> {
     y[j] = acc;                                                            \
   }
 
-template <typename Tin, typename Tout, int VEC, bool FAST>
+template <typename Tin, typename Tout, int VEC, bool FAST, bool PAD8 = false>
 __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin* __restrict__ src,
                                               const float* __restrict__ alpha_log, const float* __restrict__ beta_log,
                                               const Taps& taps, int B, int64_t T, int C, int ld, int L, int nseg, int nseg_head,
@@ -96,6 +105,7 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
   const int seg = (int)(rest % nseg);
   const int b = (int)(rest / nseg);
   const int c0 = pair * VEC;
+  const bool zpad = PAD8 && VEC == 2 && pair == P - 1;   // see store_pad8
 
   float a[VEC], ib[VEC];
 #pragma unroll
@@ -138,6 +148,7 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
         float y[VEC];
         BVG_ACT_DOWN(s, V, taps, y)
         VecIO<Tout, VEC>::store(op, y);
+        if (zpad) store_pad8(op);
         op += ld;
       }
     }
@@ -156,6 +167,7 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
         for (int j = 0; j < VEC; ++j) { V[(2 * s + 10) % 12][j] = vo[j]; V[(2 * s + 11) % 12][j] = ve[j]; }
         BVG_ACT_DOWN(s, V, taps, y)
         VecIO<Tout, VEC>::store(op, y);
+        if (zpad) store_pad8(op);
         op += ld;
       }
     }
@@ -203,7 +215,10 @@ __device__ __forceinline__ void act1d_cl_body(Tout* __restrict__ dst, const Tin*
       }
       float y[VEC];
       BVG_ACT_DOWN(s, V, taps, y)
-      if (t >= t0 && t < t1) VecIO<Tout, VEC>::store(dp + t * ld, y);
+      if (t >= t0 && t < t1) {
+        VecIO<Tout, VEC>::store(dp + t * ld, y);
+        if (zpad) store_pad8(dp + t * ld);
+      }
     }
   }
 }
@@ -261,6 +276,7 @@ template <> struct PairIO<__nv_bfloat16> {
       _Pragma("unroll") for (int k = 1; k < 12; ++k)                                       \
         acc = fma2(tp.d[k < 6 ? k : 11 - k], V[(2 * (S) + k) % 12], acc);                  \
       PairIO<Tout>::store(op, acc);                                                        \
+      if (PAD8 && zpad) store_pad8(op);                                                    \
       op += ld;                                                                             \
     }                                                                                      \
   }
@@ -277,7 +293,7 @@ constexpr int kPackedThreads = 128;
 #define BVG_ACT_MINBLK 6       // __launch_bounds__ minimum blocks per SM: 80 registers, 24 warps per SM - measured 10 % faster
                                // than the unconstrained 96-register build (5 blocks); 7-8 blocks spill and give it back
 #endif
-template <typename Tin, typename Tout, bool FAST>
+template <typename Tin, typename Tout, bool FAST, bool PAD8>
 __global__ void __launch_bounds__(kPackedThreads, BVG_ACT_MINBLK)
 act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
                        const float* __restrict__ beta_log, const TapsPacked tp, int B, int64_t T, int C, int ld, int L,
@@ -286,7 +302,7 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
   if ((int)blockIdx.x >= main_blocks) {
     // the last blocks of the grid take the sequence ends (short segments, scalar edge-aware path): they run
     // beside the interior blocks instead of as a separate ~10 us launch behind them
-    act1d_cl_body<Tin, Tout, 2, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, head_len, nseg_edge, nseg_head, tail_start,
+    act1d_cl_body<Tin, Tout, 2, FAST, PAD8>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, head_len, nseg_edge, nseg_head, tail_start,
                                       nitems_edge, (int64_t)(blockIdx.x - main_blocks) * blockDim.x + threadIdx.x);
     return;
   }
@@ -298,6 +314,7 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
   const int seg = (int)(rest % nseg_int);
   const int b = (int)(rest / nseg_int);
   const int c0 = pair * 2;
+  const bool zpad = PAD8 && pair == P - 1;   // see store_pad8
   SnakePair<FAST> sn;
   sn.init(__ldg(alpha_log + c0), __ldg(alpha_log + c0 + 1), __ldg(beta_log + c0), __ldg(beta_log + c0 + 1));
 
@@ -350,6 +367,7 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
   constexpr int kEdge = 13;   // 6n-5, >= 5
   if (!vec2) {
     // odd channel count / unaligned: scalar kernel over everything
+    if (ld > C) BVG_FAIL(BVG_EINVAL, "act1d_cl: a row pitch wider than the channel count needs even channels and aligned rows");
     static const int kSegLens[] = {253, 127, 61, 31, 13};
     int L = kSegLens[4];
     for (int i = 0; i < 5; ++i)
@@ -390,12 +408,18 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
     const int64_t main_blocks = ceil_div(nitems, kPackedThreads);
     const int64_t blocks = main_blocks + ceil_div(nitems_edge, kPackedThreads);
     if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
-    act1d_cl_packed_kernel<Tin, Tout, FAST><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
-        (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, ld, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
-        nseg, nseg_head, tail_start, nitems_edge);
+    if (ld > C)
+      act1d_cl_packed_kernel<Tin, Tout, FAST, true><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
+          (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, ld, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
+          nseg, nseg_head, tail_start, nitems_edge);
+    else
+      act1d_cl_packed_kernel<Tin, Tout, FAST, false><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
+          (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, ld, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
+          nseg, nseg_head, tail_start, nitems_edge);
     BVG_LAUNCHED();
     return BVG_OK;
   }
+  if (ld > C) BVG_FAIL(BVG_EINVAL, "act1d_cl: a row pitch wider than the channel count needs T >= 49");
   const int64_t blocks = ceil_div(nitems_edge, threads);
   if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
   act1d_cl_kernel<Tin, Tout, 2, FAST><<<(unsigned)blocks, threads, 0, st>>>(
@@ -411,6 +435,10 @@ int act1d_cl_launch(void* dst, const void* src, const float* alpha_log, const fl
   if (B <= 0 || T <= 0 || C <= 0) return BVG_OK;
   if (ld <= 0) ld = C;
   if (ld < C) BVG_FAIL(BVG_EINVAL, "act1d_cl: row pitch %d < channels %d", ld, C);
+  // ld > C: exactly 8 pad channels per row are supported (zero-filled, store_pad8); rows must then be 16-byte aligned
+  const int out_es = out_dtype == BVG_BF16 ? 2 : 4;
+  if (ld > C && (ld != C + 8 || (C & 1) || (ld * out_es) % 16 || (C * out_es) % 16 || reinterpret_cast<uintptr_t>(dst) % 16))
+    BVG_FAIL(BVG_EINVAL, "act1d_cl: unsupported row pitch %d for %d channels", ld, C);
   typedef __nv_bfloat16 bf;
   if (in_dtype == BVG_F32 && out_dtype == BVG_F32)
     return fast ? launch_cl<float, float, true>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, st)

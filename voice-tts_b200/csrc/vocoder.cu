@@ -302,10 +302,11 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   // algorithmic bytes: one read + one write of the unpadded tensor
   ProfScope ps(v, st, CAT_ACT, (double)B * T * a.C * (dtype_size(in_dt) + dtype_size(out_dt)));
   ps.cin = a.C; ps.cout = a.C; ps.k = (int)dtype_size(in_dt); ps.dil = (int)dtype_size(out_dt); ps.rows = (long long)B * T;
-  // all Cp channels are processed: pad channels (alpha = beta = 0, input 0) come out as exact zeros, which the zero
-  // weight columns of the next conv need (a stale NaN bit pattern times 0 would poison the accumulator).  Skipping them
-  // (C real channels, row pitch Cp) was measured: 0.3 ms per step at the 24-channel stage - not worth a zero-fill pass.
-  return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, a.Cp, in_dt, out_dt, fast, st, a.Cp);
+  // with exactly 8 pad channels (the 24 -> 32 channel last stage) only the real channels go through the FIRs and the snake;
+  // the thread of the last real pair also stores exact zeros into the pad channels, which the zero weight columns of the
+  // next conv need (a stale NaN bit pattern times 0 would poison the accumulator).  Saves a quarter of that stage's work.
+  const int Cact = (a.Cp == a.C + 8 && !(a.C & 1) && T >= 64) ? a.C : a.Cp;   // (short sequences: all-scalar launch, all channels)
+  return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
 }
 
 // ---- debug: order-independent checksums of intermediate tensors (BVG_DBG_SUMS=1), printed per forward ----
