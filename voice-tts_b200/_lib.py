@@ -68,6 +68,8 @@ def load():
             "or `python voice-tts_b200/build.py`; there is no CPU/PyTorch fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
+        if not hasattr(lib, name) and os.environ.get("BVG_LIB_NAME"):   # debug builds of older revisions
+            continue
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -285,7 +285,10 @@ template <> struct PairIO<__nv_bfloat16> {
 // handled by the scalar kernel's generic path in a second (tiny) launch.
 // 256-thread blocks: one block (8 warps, <= 96 registers) fits on an SM next to a persistent
 // tcgen05 conv CTA of another AMP block (vocoder.cu: blocks of a stage run on separate streams).
-constexpr int kPackedThreads = 128;
+#ifndef BVG_ACT_THREADS
+#define BVG_ACT_THREADS 128
+#endif
+constexpr int kPackedThreads = BVG_ACT_THREADS;
 #ifndef BVG_ACT_PF
 #define BVG_ACT_PF 6           // rows of run-ahead loads per thread (6 or 12)
 #endif

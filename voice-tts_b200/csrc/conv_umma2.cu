@@ -444,7 +444,8 @@ static bool u2_plan(const ConvArgs& a, U2Params& p) {
   for (int nt = p.CB; nt <= nt_max; nt += p.CB) {
     // measured (u2dbg, 384/768-channel layers): an MMA with N in (128, 256] takes ~150 cycles in the running
     // pipeline whatever N is (operand fetch + TMA fill share the shared-memory ports), so wide tiles win
-    const double t_mma = ksteps * (nt > 128 ? 150.0 : (nt / 2.0 > 90.0 ? nt / 2.0 : 90.0));
+    static const bool old_plan = getenv("BVG_U2_OLDPLAN") != nullptr;   // debug: the pre-measurement cost model
+    const double t_mma = ksteps * ((nt > 128 && !old_plan) ? 150.0 : (nt / 2.0 > 90.0 ? nt / 2.0 : 90.0));
     const double t_mem = nt * ((double)CW * (es + 4 * nin) + (double)a.Cin_p * 2 / ncot) / 22.0;
     const double t_epi = (double)(nt / p.CB) * (ncol * 8 + 250);
     double t = t_mma > t_mem ? t_mma : t_mem;
