@@ -170,6 +170,9 @@ int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
 /* options: "graph" (0/1, CUDA-graph the layer sequence), "conv_impl" (0 auto, 1 simt, 2 tcgen05),
  * "fast_sin" (0/1), "workspace_mb" (micro-batching cap), "profile" (0/1) */
 int bvg_set_option(bvg_vocoder* v, const char* key, int value);
+/* Debug only: filler kernel for co-residency experiments (mode 0: FMA spin, mode 1: streams `scratch`). */
+int bvg_debug_spin(int blocks, int threads, int iters, int mode, float* scratch, int64_t scratch_elems, bvg_stream_t stream);
+
 /* per-kernel CUDA-event timing (set option "profile"=1 first; disables graph replay while on):
  * category 0 = tcgen05 conv, 1 = SIMT conv, 2 = fused activation, 3 = other.  Returns the summed
  * duration [ms], the summed algorithmic work (flops for convs, bytes for activations) and the

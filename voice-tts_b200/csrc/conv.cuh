@@ -51,6 +51,7 @@ int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, i
 int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, const float* w, float bias, int B,
                      int Cp, int64_t T, int use_tanh, cudaStream_t st);
 int f32_to_i16(int16_t* dst, const float* src, int64_t n, cudaStream_t st);
+int debug_spin_launch(int blocks, int threads, int iters, int mode, float* scratch, int64_t n, cudaStream_t st);
 
 // channel padding of the channels-last tensors (the tcgen05 kernels accept multiples of 8 - the zero fill of their
 // 64-channel TMA boxes completes the last K step - but 16 keeps every bf16 row a multiple of 32 bytes)

@@ -48,8 +48,14 @@ constexpr int U2_X_STAGES = 2;
 constexpr int U2_MAX_X_ROWS = 320;
 constexpr int U2_X_STAGE_BYTES = U2_MAX_X_ROWS * 128;
 constexpr int U2_OUT_SLOTS = 2;
-constexpr int U2_SMEM_BYTES = 1024 + U2_AIN_SLOTS * U2_SLOT_BYTES + U2_X_STAGES * U2_X_STAGE_BYTES +
-                              U2_OUT_SLOTS * U2_SLOT_BYTES + 512;
+constexpr int U2_SMEM_USED = 1024 + U2_AIN_SLOTS * U2_SLOT_BYTES + U2_X_STAGES * U2_X_STAGE_BYTES +
+                             U2_OUT_SLOTS * U2_SLOT_BYTES + 512;
+// The launch asks for the whole 227 KB opt-in maximum: with the 1 KB the system reserves per CTA that is the SM's entire
+// 228 KB carve-out, so no CTA of any other kernel (not even one without shared memory) can become resident beside this
+// persistent CTA.  Co-resident activation blocks of another stream were the one condition under which older revisions
+// returned corrupted tiles; owning the SM costs nothing and removes the exposure.
+constexpr int U2_SMEM_BYTES = 227 * 1024;
+static_assert(U2_SMEM_USED <= U2_SMEM_BYTES, "shared-memory plan exceeds the opt-in maximum");
 
 struct U2Params {
   const float* bias;

@@ -45,8 +45,10 @@ constexpr int UA_MAX_X_ROWS = 320;
 constexpr int UA_X_STAGE_BYTES = UA_MAX_X_ROWS * 128;
 constexpr int UA_LEAD = 6;                           // columns before the first output: 5 halo + 1 (bodies of 6 steps)
 constexpr int UA_STAGE_BYTES = 2 * 30 * 32 * 2;      // one staging buffer: 2 sub-segments x 30 rows x 32 channels x bf16
-constexpr int UA_SMEM_BYTES = 1024 + UA_A_SLOTS * UA_SLOT_BYTES + UA_X_STAGES * UA_X_STAGE_BYTES +
-                              UA_EPI_WARPS * 2 * UA_STAGE_BYTES + 512;
+constexpr int UA_SMEM_USED = 1024 + UA_A_SLOTS * UA_SLOT_BYTES + UA_X_STAGES * UA_X_STAGE_BYTES +
+                             UA_EPI_WARPS * 2 * UA_STAGE_BYTES + 512;
+constexpr int UA_SMEM_BYTES = 227 * 1024;            // the whole opt-in maximum: this CTA owns the SM (see conv_umma2.cu)
+static_assert(UA_SMEM_USED <= UA_SMEM_BYTES, "shared-memory plan exceeds the opt-in maximum");
 
 struct UAParams {
   const float* bias;
