@@ -199,3 +199,34 @@ def test_no_cpu_fallback(pkg, synth, cfg):
         m(torch.zeros(1, h["num_mels"] + 1, 4, device=DEV))
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, h["num_mels"], 4, device=DEV, dtype=torch.float16))
+
+
+OPTION_SETS = [
+    {"fuse_act": 0, "fuse_res": 0},                 # every conv and activation as its own launch
+    {"fuse_act": 2, "fuse_res": 0},                 # conv1 + a2 fused everywhere
+    {"fuse_act": 2, "fuse_res": 2},                 # + conv2 + residual + next a1 fused everywhere
+    {"streams": 3}, {"streams": 2, "graph": 1}, {"graph": 1},
+]
+
+
+@pytest.mark.parametrize("opts", OPTION_SETS, ids=[",".join("%s=%d" % kv for kv in o.items()) for o in OPTION_SETS])
+def test_full_generator_bf16_option_matrix(pkg, golden, full_model_sd, opts):
+    """Every dispatch the plan can take (fusion policies forced on/off, multi-stream AMP blocks, CUDA graph replay)
+    meets the bf16 bar against the reference golden; schedules that do not change the arithmetic (streams, graph) are
+    bit-identical to the default one."""
+    h, sd = full_model_sd
+    g = golden("generators")
+    mel = t(g["full.mel"]).to(DEV)
+    ref = t(g["full.wav"])
+    base = make(pkg, h, sd, "bf16")
+    m = make(pkg, h, sd, "bf16", **opts)
+    with torch.no_grad():
+        wav0 = base(mel)
+        wav = m(mel)
+        wav_again = m(mel)     # second call: graph replay / reused streams and workspace
+    snr = O.snr_db(ref, wav.cpu())
+    print("full bf16 %s: SNR %.2f dB" % (opts, snr))
+    assert snr >= 40.0
+    assert torch.equal(wav, wav_again)
+    if "fuse_act" not in opts and "fuse_res" not in opts:
+        assert torch.equal(wav, wav0)
