@@ -230,3 +230,28 @@ def test_full_generator_bf16_option_matrix(pkg, golden, full_model_sd, opts):
     assert torch.equal(wav, wav_again)
     if "fuse_act" not in opts and "fuse_res" not in opts:
         assert torch.equal(wav, wav0)
+
+
+def test_full_generator_30s_utterances(pkg, synth, full_model_sd):
+    """BASELINE config 4 shape (30 s utterances, 2 584 mel frames): waveform length, range, batch independence and
+    the chunked long-audio path (split_chunks with the 34-frame receptive-field halo) against the one-shot forward."""
+    import importlib
+    shard = importlib.import_module("voice-tts_b200.shard")
+    h, sd = full_model_sd
+    m = make(pkg, h, sd, "bf16")
+    mel = synth.make_mel(3, 80, 2584).to(DEV)
+    with torch.no_grad():
+        wav = m(mel)
+        one = m(mel[2:3].contiguous())
+    assert wav.shape == (3, 1, 2584 * 256)
+    assert torch.isfinite(wav).all() and float(wav.abs().max()) <= 1.0
+    assert torch.equal(wav[2:3], one)
+    # long audio cut along time: interior samples of every chunk equal the one-shot result exactly
+    pieces = []
+    for (lo, hi, keep_lo, keep_hi) in shard.split_chunks(2584, 700, halo=34):
+        with torch.no_grad():
+            w = m(mel[:1, :, lo:hi].contiguous())
+        pieces.append(w[..., keep_lo * 256:keep_hi * 256])   # keep_* are relative to the chunk start
+    stitched = torch.cat(pieces, dim=-1)
+    assert stitched.shape == wav[:1].shape
+    assert torch.equal(stitched, wav[:1])
