@@ -73,7 +73,6 @@ struct U2Params {
   int w_resident;    // all k*nchunks weight tiles are loaded once and stay in the ring slots
   int CB;            // time rows per epilogue block = NCOL * 2 * rep
   long long* dbg;    // optional per-role wait-cycle counters of CTA 0 (BVG_U2_DBG=1)
-  int tm_mode;       // debug (BVG_U2_TMMODE): 0 prefetch.tensormap, 1 nothing, 2 fence.proxy.tensormap acquire
 };
 
 struct U2Tile {
@@ -139,19 +138,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     for (int i = 0; i < U2_IN_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], U2_EPI_WARPS); }
     for (int i = 0; i < U2_OUT_SLOTS; ++i) { mbar_init(&out_ready[i], U2_EPI_WARPS); mbar_init(&out_free[i], 1); }
     mbar_fence_init();
-    if (p.tm_mode == 0) {
-      tma_prefetch_desc(&tmap_x);
-      tma_prefetch_desc(&tmap_w);
-      tma_prefetch_desc(&tmap_out);
-      if (NIN >= 1) tma_prefetch_desc(&tmap_res);
-      if (NIN == 2) tma_prefetch_desc(&tmap_acc);
-    } else if (p.tm_mode == 2) {
-      asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(&tmap_x) : "memory");
-      asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(&tmap_w) : "memory");
-      asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(&tmap_out) : "memory");
-      if (NIN >= 1) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(&tmap_res) : "memory");
-      if (NIN == 2) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(&tmap_acc) : "memory");
-    }
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_out);
+    if (NIN >= 1) tma_prefetch_desc(&tmap_res);
+    if (NIN == 2) tma_prefetch_desc(&tmap_acc);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -450,8 +441,7 @@ static bool u2_plan(const ConvArgs& a, U2Params& p) {
   for (int nt = p.CB; nt <= nt_max; nt += p.CB) {
     // measured (u2dbg, 384/768-channel layers): an MMA with N in (128, 256] takes ~150 cycles in the running
     // pipeline whatever N is (operand fetch + TMA fill share the shared-memory ports), so wide tiles win
-    static const bool old_plan = getenv("BVG_U2_OLDPLAN") != nullptr;   // debug: the pre-measurement cost model
-    const double t_mma = ksteps * ((nt > 128 && !old_plan) ? 150.0 : (nt / 2.0 > 90.0 ? nt / 2.0 : 90.0));
+    const double t_mma = ksteps * (nt > 128 ? 150.0 : (nt / 2.0 > 90.0 ? nt / 2.0 : 90.0));
     const double t_mem = nt * ((double)CW * (es + 4 * nin) + (double)a.Cin_p * 2 / ncot) / 22.0;
     const double t_epi = (double)(nt / p.CB) * (ncol * 8 + 250);
     double t = t_mma > t_mem ? t_mma : t_mem;
@@ -504,8 +494,6 @@ int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   }
   const int sms = umma_sm_count();
   const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
-  static const int tm_mode = getenv("BVG_U2_TMMODE") ? atoi(getenv("BVG_U2_TMMODE")) : 0;
-  p.tm_mode = tm_mode;
   static const bool want_dbg = getenv("BVG_U2_DBG") != nullptr;
   static long long* dbg_buf = nullptr;
   p.dbg = nullptr;

@@ -309,40 +309,6 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
 }
 
-// ---- debug: order-independent checksums of intermediate tensors (BVG_DBG_SUMS=1), printed per forward ----
-__global__ void dbg_sum_kernel(const uint32_t* __restrict__ p, size_t n, unsigned long long* out) {
-  unsigned long long acc = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t w = __ldcg(p + i);
-    acc += (unsigned long long)w * (unsigned long long)((i % 1000003u) + 1u);
-  }
-  atomicAdd(out, acc);
-}
-struct DbgSums {
-  bool on = getenv("BVG_DBG_SUMS") != nullptr;
-  unsigned long long* dev = nullptr;
-  std::vector<std::string> tags;
-  void add(const void* p, size_t bytes, const char* tag, int a, int b, int c, cudaStream_t st) {
-    if (!on) return;
-    if (!dev) { cudaMalloc((void**)&dev, 4096 * 8); }
-    if (tags.size() >= 4096) return;
-    const size_t idx = tags.size();
-    char buf[96]; snprintf(buf, sizeof(buf), "%s[%d,%d,%d]", tag, a, b, c);
-    tags.push_back(buf);
-    cudaMemsetAsync(dev + idx, 0, 8, st);
-    dbg_sum_kernel<<<296, 256, 0, st>>>((const uint32_t*)p, bytes / 4, dev + idx);
-  }
-  void flush() {
-    if (!on || tags.empty()) return;
-    cudaDeviceSynchronize();
-    std::vector<unsigned long long> h(tags.size());
-    cudaMemcpy(h.data(), dev, tags.size() * 8, cudaMemcpyDeviceToHost);
-    for (size_t i = 0; i < tags.size(); ++i) fprintf(stderr, "dbgsum %s %016llx\n", tags[i].c_str(), h[i]);
-    tags.clear();
-  }
-};
-static DbgSums g_dbg;
-
 // internal streams / events for the concurrent AMP blocks (created on first use)
 static int ensure_streams(bvg_vocoder* v) {
   for (int i = 0; i < 3; ++i) {
@@ -380,12 +346,8 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
       // block -> (stream, buffer set): the last block on the caller's stream, the others round-robin on aux streams
       const int slot = nb > 1 ? (j == v->nk - 1 ? nb - 1 : j % (nb - 1)) : 0;
       cudaStream_t sj = (nb > 1 && j != v->nk - 1) ? v->aux[slot] : st;
-      static const bool dbg_one_aux = getenv("BVG_DBG_ONE_AUX") != nullptr;   // debug: all aux blocks on aux[0], own buffers
-      if (dbg_one_aux && sj != st) sj = v->aux[0];
       if (nb > 1) prof_break(v);
       if (sj != st) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_fork, 0));
-      static const int dbg_serial = getenv("BVG_SERIAL_BLOCKS") ? atoi(getenv("BVG_SERIAL_BLOCKS")) : 0;   // debug: bit j = block j starts after block j-1
-      if (((dbg_serial >> j) & 1) && nb > 1 && j > 0) BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0));
       const float* cur = bf.x;
       bool a1_ready = false;     // a1 of this unit already came out of the previous unit's fused conv2
       for (int l = 0; l < v->nd; ++l) {
@@ -397,18 +359,15 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
         }
         a1_ready = false;
         const size_t nel = (size_t)B * T * v->Cp[i + 1];
-        g_dbg.add(bf.a1[slot], nel * dtype_size(adt), "a1", i, j, l, sj);
         if (can_fuse_conv_act(v, v->convs1[ci], bf.a1[slot], bf.a2[slot], B, T)) {
           rc = run_conv_act(v, v->convs1[ci], v->acts[ai + 1], bf.a1[slot], bf.a2[slot], B, T, sj);
           if (rc) return rc;
         } else {
           rc = run_conv(v, v->convs1[ci], bf.a1[slot], adt, bf.m[slot], adt, nullptr, nullptr, 1.f, B, T, sj);
           if (rc) return rc;
-          g_dbg.add(bf.m[slot], nel * dtype_size(adt), "m", i, j, l, sj);
           rc = run_act(v, v->acts[ai + 1], bf.m[slot], adt, bf.a2[slot], adt, B, T, sj);
           if (rc) return rc;
         }
-        g_dbg.add(bf.a2[slot], nel * dtype_size(adt), "a2", i, j, l, sj);
         if (l < v->nd - 1) {
           float* ynext = (l & 1) ? bf.y2[slot] : bf.y[slot];
           if (can_fuse_conv_res_act(v, v->convs2[ci], bf.a2[slot], bf.a1[slot], cur, B, T)) {
@@ -418,14 +377,12 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
             rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, ynext, BVG_F32, cur, nullptr, 1.f, B, T, sj);
           }
           cur = ynext;
-          g_dbg.add(ynext, nel * 4, "y", i, j, l, sj);
         } else {
           const bool to_next = (j == v->nk - 1) && !last_stage;
           if (nb > 1 && j > 0) { prof_break(v); BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0)); }   // XS of block j-1
           rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, to_next ? bf.nx : (void*)bf.xs, to_next ? adt : BVG_F32, cur,
                         j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, sj);
           if (rc) return rc;
-          g_dbg.add(to_next ? bf.nx : (void*)bf.xs, nel * (to_next ? dtype_size(adt) : 4), "xs", i, j, l, sj);
           if (nb > 1 && j < v->nk - 1) BVG_CUDA(cudaEventRecord(v->ev_blk[j % 3], sj));
         }
         if (rc) return rc;
@@ -517,7 +474,6 @@ int vocoder_forward(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, in
     if (rc) return rc;
   }
   v->last_launches = (int)(g_launches.load() - l0);
-  g_dbg.flush();
   return BVG_OK;
 }
 
