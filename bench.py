@@ -258,7 +258,6 @@ def main():
         model.remove_weight_norm()
     model.load_state_dict(sd)
     model = model.to(dev).eval()
-    model.set_option("profile", 1)
 
     B, T0 = args.batch, args.frames
     audio_s_step = B * T0 * HOP / SR
@@ -280,8 +279,6 @@ def main():
         for _ in range(max(args.warmup, 3)):
             wav = model(mel)
         torch.cuda.synchronize()
-        model.read_profile()  # drop warm-up records
-        model.set_option("profile", 0)
 
         def timed_steps():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -301,33 +298,39 @@ def main():
         n0 = _lib.launch_count()
         ms, wav = timed_steps()
         launches = _lib.launch_count() - n0
-        # ---- the same K steps again with one CUDA-event pair per kernel on the launch stream (roofline / time split).
-        #      An event between two launches keeps the next kernel from being issued while the previous one drains
-        #      (~5-9 us per launch, 2-4 % of the step), so the headline comes from the un-instrumented pass above and
-        #      this pass reports its own ms_per_step beside the per-kernel sums. ----
+        # ---- the same K steps again, serial schedule (streams = 1), with one CUDA-event pair per kernel on the launch
+        #      stream (roofline / time split).  An event between two launches keeps the next kernel from being issued
+        #      while the previous one drains (~5-9 us per launch, 2-4 % of the step), and per-kernel times only add up
+        #      when kernels do not overlap, so the headline comes from the un-instrumented default pass above and this
+        #      pass reports its own ms_per_step beside the per-kernel sums. ----
+        wav_default = wav.clone()
+        model.set_option("streams", 1)
+        for _ in range(2):
+            model(mel)
+        ms_serial, wav_s = timed_steps()
+        serial_identical = bool(torch.equal(wav_s, wav_default))
         model.set_option("profile", 1)
+        model(mel)
+        model.read_profile()
         ms_prof, _ = timed_steps()
         clocks = sampler.stop() if rank == 0 else None
         prof = model.read_profile()
-
-        # ---- opt-in schedule: the 3 AMP blocks of a stage on 3 streams; reported beside the
-        #      headline, never instead of it, and only if its waveform is bit-identical to the serial one ----
         model.set_option("profile", 0)
-        wav_serial = wav.clone()
         model.set_option("streams", 3)
-        for _ in range(3):
-            wav3 = model(mel)
+        del wav_default, wav_s
+
+        # ---- latency of ONE utterance (BASELINE configs[0] shape: 172 frames = 2 s), the way infer_v2 calls the vocoder ----
+        mel1 = mel[:1, :, :172].contiguous()
+        for _ in range(5):
+            model(mel1)
         barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        for _ in range(args.steps):
-            wav3 = model(mel)
-        e3.record()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for _ in range(50):
+            model(mel1)
+        e5.record()
         barrier()
-        ms3 = max_over_ranks(e2.elapsed_time(e3))
-        streams3_identical = bool(torch.equal(wav3, wav_serial))
-        model.set_option("streams", 1)
-        del wav_serial, wav3
+        ms_one = max_over_ranks(e4.elapsed_time(e5)) / 50
 
         # ---- end to end through the host-buffer C ABI call ----
         model.set_option("profile", 0)
@@ -386,9 +389,11 @@ def main():
                                    "activation": a_ms / args.steps, "other": o_ms / args.steps},
         "x_realtime_per_gpu": value / world,
         "profile_pass_ms_per_step": ms_prof / args.steps,
-        "opt_in_streams3": {"value": world * audio_s_step * args.steps / (ms3 * 1e-3), "unit": UNIT,
-                            "ms_per_step": ms3 / args.steps, "bit_identical_to_serial": streams3_identical,
-                            "note": "bvg_set_option('streams', 3): AMP blocks of a stage on separate streams; off by default"},
+        "serial_schedule": {"value": world * audio_s_step * args.steps / (ms_serial * 1e-3), "unit": UNIT,
+                            "ms_per_step": ms_serial / args.steps, "bit_identical_to_default": serial_identical,
+                            "note": "bvg_set_option('streams', 1); the default runs the 3 AMP blocks of a stage on 3 streams"},
+        "single_utterance": {"frames": 172, "audio_s": 172 * HOP / SR, "ms": ms_one,
+                             "x_realtime": 172 * HOP / SR / (ms_one * 1e-3)},
     }
 
     if rank == 0 and not args.no_cpu_baseline and world >= 1:

@@ -171,8 +171,8 @@ int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
  * "fast_sin" (0/1), "workspace_mb" (micro-batching cap), "profile" (0/1: one CUDA-event pair per launch, read back with
  * bvg_profile_read), "fuse_act" (0 off, 1 measured policy, 2 always: conv1 + following activation in one kernel),
  * "fuse_res" / "fuse_res_min_kc" (conv2 + residual + next activation in one kernel: 0 off, 1 when k*Cin >= min_kc,
- * 2 always), "streams" (1 serial [default]; 2-4: the AMP blocks of a stage on separate internal streams, result
- * bit-identical), "umma_variant" (debug).  Options that change the workspace layout drop captured graphs. */
+ * 2 always), "streams" (3 [default]: the AMP blocks of a stage on separate internal streams that fork from and join the caller's
+ * stream; 1: serial; the result is bit-identical either way), "umma_variant" (debug).  Options that change the workspace layout drop captured graphs. */
 int bvg_set_option(bvg_vocoder* v, const char* key, int value);
 /* Debug only: filler kernel for co-residency experiments (mode 0: FMA spin, mode 1: streams `scratch`). */
 int bvg_debug_spin(int blocks, int threads, int iters, int mode, float* scratch, int64_t scratch_elems, bvg_stream_t stream);

@@ -205,7 +205,7 @@ OPTION_SETS = [
     {"fuse_act": 0, "fuse_res": 0},                 # every conv and activation as its own launch
     {"fuse_act": 2, "fuse_res": 0},                 # conv1 + a2 fused everywhere
     {"fuse_act": 2, "fuse_res": 2},                 # + conv2 + residual + next a1 fused everywhere
-    {"streams": 3}, {"streams": 2, "graph": 1}, {"graph": 1},
+    {"streams": 1}, {"streams": 2, "graph": 1}, {"streams": 3, "graph": 1}, {"graph": 1},
 ]
 
 

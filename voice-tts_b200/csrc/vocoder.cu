@@ -64,7 +64,7 @@ struct bvg_vocoder {
   int opt_fuse_res = 1;            // conv2 of an AMP unit adds the residual AND applies the next unit's first activation (bf16 mode)
   int opt_fuse_act = 1;            // conv1 of an AMP unit applies the following activation in its epilogue (bf16 mode)
   int fuse_res_min_kc = 4096;      // smallest k * Cin whose conv2 takes the fused residual + activation epilogue
-  int opt_streams = 1;             // AMP blocks of one stage run on up to this many streams (1 = serial; >1 experimental)
+  int opt_streams = 3;             // AMP blocks of one stage run on up to this many streams (1 = serial); see DESIGN.md 8.5
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // internal streams for AMP blocks 0 .. nk-2
   cudaEvent_t ev_fork = nullptr, ev_blk[3] = {nullptr, nullptr, nullptr};
   int64_t opt_ws_cap_mb = 24 * 1024;
