@@ -214,9 +214,89 @@ __global__ void conv_post_kernel(Tout* __restrict__ dst, const Tin* __restrict__
   }
 }
 
+// Tiled variant: the 256 + 6 input rows of a block are staged in shared memory once (coalesced 16-byte ld.global.cg), so
+// every row is fetched from L2 once instead of 7 times; rows are padded by 16 bytes, which makes the per-thread 16-byte
+// reads (thread t reads row t + j) conflict-free for 64- and 128-byte rows.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256)
+conv_post_tiled_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ w, float bias, int Cp,
+                       int64_t T, int use_tanh) {
+  extern __shared__ __align__(16) unsigned char cp_smem[];
+  float* sw = reinterpret_cast<float*>(cp_smem);                 // [7][Cp]
+  const int row_bytes = Cp * (int)sizeof(Tin);
+  const int pitch = row_bytes + 16;
+  unsigned char* tile = cp_smem + ((7 * Cp * 4 + 15) & ~15);     // [262][pitch]
+  for (int i = threadIdx.x; i < 7 * Cp; i += 256) sw[i] = w[i];
+  const int b = blockIdx.y;
+  const int64_t t0 = (int64_t)blockIdx.x * 256;
+  const unsigned char* s = reinterpret_cast<const unsigned char*>(src) + (int64_t)b * T * row_bytes;
+  const int vec_per_row = row_bytes / 16;
+  for (int i = threadIdx.x; i < 262 * vec_per_row; i += 256) {
+    const int r = i / vec_per_row, v = i % vec_per_row;
+    const int64_t tt = t0 - 3 + r;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);                      // rows outside [0, T): the conv's zero padding
+    if (tt >= 0 && tt < T) val = BVG_LDG(reinterpret_cast<const uint4*>(s + tt * row_bytes) + v);
+    *reinterpret_cast<uint4*>(tile + r * pitch + v * 16) = val;
+  }
+  __syncthreads();
+  const int64_t t = t0 + threadIdx.x;
+  if (t >= T) return;
+  float acc = bias;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const unsigned char* row = tile + (threadIdx.x + j) * pitch;
+    for (int c = 0; c < Cp; c += 8) {
+      float v[8];
+      if (sizeof(Tin) == 2) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + c * 2);
+        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[2 * q] = __uint_as_float(r[q] << 16);
+          v[2 * q + 1] = __uint_as_float(r[q] & 0xffff0000u);
+        }
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(row + c * 4);
+        const float4 bq = *reinterpret_cast<const float4*>(row + c * 4 + 16);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(sw[j * Cp + c + q], v[q], acc);
+    }
+  }
+  acc = use_tanh ? tanhf(acc) : fminf(fmaxf(acc, -1.0f), 1.0f);
+  if (sizeof(Tout) == 2) {
+    float q = fminf(fmaxf(32767.0f * acc, -32767.0f), 32767.0f);
+    reinterpret_cast<int16_t*>(dst)[(int64_t)b * T + t] = (int16_t)q;
+  } else {
+    reinterpret_cast<float*>(dst)[(int64_t)b * T + t] = acc;
+  }
+}
+
+template <typename Tin, typename Tout>
+static bool conv_post_tiled(void* dst, const void* src, const float* w, float bias, int B, int Cp, int64_t T, int use_tanh,
+                            cudaStream_t st) {
+  const int smem = ((7 * Cp * 4 + 15) & ~15) + 262 * (Cp * (int)sizeof(Tin) + 16);
+  if (smem > 48 * 1024 || Cp % 8 != 0 || (reinterpret_cast<uintptr_t>(src) & 15)) return false;
+  dim3 grid((unsigned)ceil_div(T, 256), (unsigned)B);
+  conv_post_tiled_kernel<Tin, Tout><<<grid, 256, smem, st>>>((Tout*)dst, (const Tin*)src, w, bias, Cp, T, use_tanh);
+  return true;
+}
+
 int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, const float* w, float bias, int B,
                      int Cp, int64_t T, int use_tanh, cudaStream_t st) {
   if (B <= 0 || T <= 0) return BVG_OK;
+  {
+    bool done;
+    if (in_dtype == BVG_BF16)
+      done = out_i16 ? conv_post_tiled<__nv_bfloat16, int16_t>(dst, src, w, bias, B, Cp, T, use_tanh, st)
+                     : conv_post_tiled<__nv_bfloat16, float>(dst, src, w, bias, B, Cp, T, use_tanh, st);
+    else
+      done = out_i16 ? conv_post_tiled<float, int16_t>(dst, src, w, bias, B, Cp, T, use_tanh, st)
+                     : conv_post_tiled<float, float>(dst, src, w, bias, B, Cp, T, use_tanh, st);
+    if (done) { BVG_LAUNCHED(); return BVG_OK; }
+  }
   dim3 grid((unsigned)ceil_div(T, 256), (unsigned)B);
   const int smem = 7 * Cp * (int)sizeof(float);
   if (in_dtype == BVG_BF16) {
