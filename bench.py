@@ -227,6 +227,38 @@ def act_sweep(dev, pk):
     return rows
 
 
+def top_launch_stats(model, pk):
+    """The layer shape that costs the most time in the instrumented pass: its own achieved TFLOP/s (per-launch CUDA events)."""
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), "bvg_bench_profile_%d.csv" % os.getpid())
+    try:
+        model.dump_profile(path)
+        groups = {}
+        with open(path) as f:
+            for ln in f.read().splitlines()[1:]:
+                cat, cin, cout, k, dil, rows, ms, work, rate = ln.split(",")
+                if cat != "0":
+                    continue
+                mode = int(dil) // 100
+                key = (int(cin), int(cout), int(k), mode)
+                g = groups.setdefault(key, [0, 0.0, 0.0])
+                g[0] += 1
+                g[1] += float(ms)
+                g[2] += float(work)
+        os.remove(path)
+        if not groups:
+            return None
+        key, (n, ms, work) = max(groups.items(), key=lambda kv: kv[1][1])
+        tf = work / (ms * 1e-3) / 1e12
+        kind = {0: "plain epilogue", 1: "following Activation1d in the epilogue", 2: "residual + following Activation1d in the epilogue"}[key[3]]
+        return {"layer": "Conv1d %d->%d k=%d (%s)" % (key[0], abs(key[1]), key[2], kind), "launches": n,
+                "avg_launch_ms": round(ms / n, 4), "achieved": round(tf, 1), "unit": "TFLOP/s",
+                "frac_of_sustained_peak": round(tf / pk["bf16_tflops_sustained"], 4),
+                "frac_of_burst_peak": round(tf / pk["bf16_tflops"], 4)}
+    except Exception as exc:  # diagnostics only
+        return {"error": str(exc)}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -314,6 +346,9 @@ def main():
         model.read_profile()
         ms_prof, _ = timed_steps()
         clocks = sampler.stop() if rank == 0 else None
+        top_launch = None
+        if rank == 0:
+            top_launch = top_launch_stats(model, pk)
         prof = model.read_profile()
         model.set_option("profile", 0)
         model.set_option("streams", 3)
@@ -364,6 +399,8 @@ def main():
                 "measured": "one CUDA-event pair per launch on the launch stream, summed over a second pass of the same K steps",
                 "share_of_step": round(conv_ms / tot, 3) if tot else None, "launches": conv_n,
                 "avg_launch_ms": round(conv_ms / max(conv_n, 1), 4)}
+    if top_launch:
+        roofline["top_launch"] = top_launch
     roofline_act = {"kernel": "act1d_cl_packed_kernel (stand-alone fused up2-snakebeta-down2, channels-last; the activations fused into conv epilogues are not counted here)", "bound": "hbm",
                     "achieved": round(ach_gb, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": None,
