@@ -276,3 +276,18 @@ def test_full_generator_bf16_vs_fp32_mode_ragged_lengths(pkg, synth, full_model_
     # the sequence ends are where the edge variants of the kernels run: compare them separately
     n = min(512, T0 * 256)
     assert O.snr_db(ref[..., :n], wav[..., :n]) >= 30.0 and O.snr_db(ref[..., -n:], wav[..., -n:]) >= 30.0
+
+
+def test_forward_segments_ragged_batching(pkg, synth, full_model_sd):
+    """SURVEY section 8(f) rank 1: the per-segment vocoder calls of infer_v2 (one call per text segment) batched by length;
+    every waveform is bit-identical to the one-segment-at-a-time result."""
+    h, sd = full_model_sd
+    m = make(pkg, h, sd, "bf16")
+    lengths = [57, 130, 57, 301, 130, 57, 12]
+    mels = [synth.make_mel(1, 80, T, first_utterance=i)[0].to(DEV) for i, T in enumerate(lengths)]
+    with torch.no_grad():
+        wavs = m.forward_segments(mels)
+        singles = [m(x.unsqueeze(0))[0] for x in mels]
+    assert [tuple(w.shape) for w in wavs] == [(1, T * 256) for T in lengths]
+    for w, s in zip(wavs, singles):
+        assert torch.equal(w, s)

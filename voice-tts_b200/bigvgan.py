@@ -219,6 +219,35 @@ class BigVGAN(nn.Module):
         _lib.check(rc, "bvg_vocoder_fwd_host")
         return out
 
+    def forward_segments(self, mels):
+        """Vocode a list of segments of DIFFERENT lengths in as few launches as exactness allows.
+
+        `infer_v2.py:616-744` runs the vocoder once per text segment (`wav = self.bigvgan(vc_target.float())`).  Segments of
+        equal length are stacked into one batch; every distinct length is its own batch, because the convolutions zero-pad
+        and the activations replicate-pad at each utterance's TRUE end - padding a short mel to a common length would change
+        its last ~34 frames.  Each returned waveform is bit-identical to `self(mel)` on that segment alone (batch rows are
+        independent, tests/test_gpu_vocoder.py).  mels: tensors [num_mels, T_i] or [1, num_mels, T_i] on one CUDA device;
+        returns a list of [1, T_i * hop] tensors in the input order."""
+        if not mels:
+            return []
+        items = [m if m.dim() == 3 else m.unsqueeze(0) for m in mels]
+        for m in items:
+            if m.dim() != 3 or m.shape[0] != 1:
+                raise RuntimeError("forward_segments expects [num_mels, T] or [1, num_mels, T] tensors")
+        groups = {}
+        for i, m in enumerate(items):
+            groups.setdefault(int(m.shape[-1]), []).append(i)
+        out = [None] * len(items)
+        for T, idx in sorted(groups.items()):
+            if T == 0:
+                for i in idx:
+                    out[i] = items[i].new_empty(1, 0)
+                continue
+            wav = self.forward(torch.cat([items[i] for i in idx], dim=0).float())
+            for row, i in enumerate(idx):
+                out[i] = wav[row]
+        return out
+
     def read_profile(self):
         """{category: (ms, algorithmic work, launches)} since the last read (option profile=1)."""
         import ctypes
