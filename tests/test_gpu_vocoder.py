@@ -291,3 +291,28 @@ def test_forward_segments_ragged_batching(pkg, synth, full_model_sd):
     assert [tuple(w.shape) for w in wavs] == [(1, T * 256) for T in lengths]
     for w, s in zip(wavs, singles):
         assert torch.equal(w, s)
+
+
+@pytest.mark.parametrize("overrides", [
+    {"num_mels": 100},                                                   # the 24 kHz / 100-band sibling (Dockerfile:56)
+    {"num_mels": 80, "upsample_initial_channel": 512, "upsample_rates": [8, 4, 2], "upsample_kernel_sizes": [16, 8, 4]},
+    {"activation": "snake", "snake_logscale": False},
+], ids=["100band", "rates842_512ch", "snake_linear"])
+def test_other_configurations_vs_oracle(pkg, synth, cfg, overrides):
+    """The generator is a function of its config.json, not of the one shipped checkpoint: other band counts, upsampling
+    plans (any even rate u with kernel 2u) and the plain Snake / linear-scale variants against the oracle, both modes."""
+    h = cfg.tiny_hparams(**overrides)
+    sd = synth.make_state_dict(h, seed=11)
+    mel = synth.make_mel(2, h["num_mels"], 45)
+    ref = O.generator_forward(sd, h, mel)
+    for precision, bar in (("fp32", None), ("bf16", 33.0)):
+        m = make(pkg, h, sd, precision)
+        with torch.no_grad():
+            wav = m(mel.to(DEV)).cpu()
+        assert wav.shape == ref.shape
+        if bar is None:
+            assert (wav - ref).abs().max() <= 1e-5 * float(ref.abs().max()), overrides
+        else:
+            snr = O.snr_db(ref, wav)
+            print("%s bf16 SNR %.1f dB" % (overrides, snr))
+            assert snr >= bar
