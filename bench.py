@@ -393,8 +393,19 @@ def main():
     tensor_peak = pk["bf16_tflops_sustained"]
     ach_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     ach_gb = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
+    # DRAM traffic per launch from the committed ncu capture of one forward of the SAME workload (tools/ncu_traffic.py ->
+    # profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the kernel's launches / launches)
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
+        if B == 16 and T0 == 861 and args.precision == "bf16":
+            traffic = tj
+    except Exception:
+        pass
     roofline = {"kernel": conv_name, "bound": "tensor", "achieved": round(ach_tf, 2), "peak": tensor_peak,
-                "unit": "TFLOP/s", "frac": round(ach_tf / tensor_peak, 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(ach_tf / tensor_peak, 4),
+                "traffic": traffic.get("conv_tcgen05", {}).get("dram_bytes_per_launch") if c_n else None,
+                "traffic_note": "bytes per launch averaged over the 115 conv launches of one forward (profiles/r01_traffic.txt); operands + results of the padded tensors, no re-reads",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
                 "measured": "one CUDA-event pair per launch on the launch stream, summed over a second pass of the same K steps",
                 "share_of_step": round(conv_ms / tot, 3) if tot else None, "launches": conv_n,
@@ -403,7 +414,9 @@ def main():
         roofline["top_launch"] = top_launch
     roofline_act = {"kernel": "act1d_cl_packed_kernel (stand-alone fused up2-snakebeta-down2, channels-last; the activations fused into conv epilogues are not counted here)", "bound": "hbm",
                     "achieved": round(ach_gb, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": None,
+                    "frac": round(ach_gb / pk["hbm_gbs"], 4),
+                    "traffic": traffic.get("activation", {}).get("dram_bytes_per_launch"),
+                    "algorithmic_bytes_per_launch": round(a_bytes / max(a_n, 1), 1),
                     "share_of_step": round(a_ms / tot, 3) if tot else None, "launches": a_n}
 
     out = {
