@@ -21,6 +21,9 @@
  *   bvg_convtr1d_fwd     <- torch.nn.ConvTranspose1d as built at bigvgan.py:306-312
  *   bvg_create/..._fwd   <- BigVGAN.__init__/forward/remove_weight_norm  bigvgan.py:266-400,
  *                           called from indextts/infer_v2.py:155-158,735
+ *   bvg_vocoder_fwd_cond <- the speaker-conditioned IndexTTS-v1 generator, indextts/BigVGAN/models.py:130-250
+ *                           (`forward(x, mel_ref, lens)` :212-250 minus its ECAPA speaker encoder), called from
+ *                           indextts/infer.py:476,646 as `wav, _ = self.bigvgan(latent, auto_conditioning.transpose(1, 2))`
  *   bvg_vocoder_fwd_host <- the host round trip of indextts/infer_v2.py:735-744 (mel on host -> wav on host,
  *                           optional int16 quantisation `clamp(32767*wav)` of :740)
  */
@@ -34,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 1
+#define BVG_ABI_VERSION 2
 
 /* status codes */
 #define BVG_OK 0
@@ -93,7 +96,7 @@ int bvg_act1d_cl_fwd(void* dst, const void* src, const float* alpha_log, const f
  * and by callers that want single layers): fp32 [B,C,T] in/out, fp32 weights in
  * torch layout.  `mode` selects fp32 SIMT or bf16 tcgen05 arithmetic.
  *   conv1d   : weight [Cout, Cin, k], bias [Cout] or NULL, zero padding (k-1)*dil/2
- *   convtr1d : weight [Cin, Cout, k], k == 2*stride, padding stride/2 -> T_out = stride*T
+ *   convtr1d : weight [Cin, Cout, k], padding (k - stride)/2 with k - stride even and <= 2*stride -> T_out = stride*T
  */
 int bvg_conv1d_fwd(float* dst, const float* src, const float* weight, const float* bias,
                    int B, int Cin, int Cout, int64_t T, int k, int dilation, int mode,
@@ -136,7 +139,7 @@ typedef struct bvg_config {
   int upsample_initial_channel; /* 1536 */
   int num_upsamples;            /* <= 8 */
   int upsample_rates[8];        /* {4,4,2,2,2,2} */
-  int upsample_kernel_sizes[8]; /* {8,8,4,4,4,4}; must equal 2*rate */
+  int upsample_kernel_sizes[8]; /* {8,8,4,4,4,4}; k - rate even, 0 <= (k - rate)/2 <= rate (padding (k - rate)/2) */
   int num_kernels;              /* <= 4 */
   int resblock_kernel_sizes[4]; /* {3,7,11} */
   int num_dilations;            /* <= 4 */
@@ -147,6 +150,10 @@ typedef struct bvg_config {
   int use_bias_at_final;
   int mode;                     /* BVG_MODE_* */
   int device;                   /* CUDA device ordinal */
+  /* --- ABI 2: the speaker-conditioned v1 generator (indextts/BigVGAN/models.py:130-250); all 0 for BigVGAN v2 --- */
+  int input_channels_last;      /* 1: the input is [B, T0, num_mels] (the GPT latent, num_mels = gpt_dim; models.py:220) */
+  int cond_dim;                 /* speaker_embedding_dim; > 0 adds cond_layer(e) after conv_pre (models.py:224) */
+  int cond_each_up;             /* cond_d_vector_in_each_upsampling_layer: conds[i](e) after ups[i] (models.py:233-234) */
 } bvg_config;
 
 int bvg_create(const bvg_config* cfg, bvg_vocoder** out);
@@ -163,6 +170,12 @@ int64_t bvg_workspace_bytes(const bvg_vocoder* v, int B, int T0);
 
 /* mel [B, num_mels, T0] fp32 device -> wav [B, 1, T0*prod(rates)] fp32 device, on `stream`. */
 int bvg_vocoder_fwd(bvg_vocoder* v, const float* mel, float* wav, int B, int T0, bvg_stream_t stream);
+/* Speaker-conditioned generator (cfg.cond_dim > 0): latent [B, T0, num_mels] fp32 device (cfg.input_channels_last = 1;
+ * [B, num_mels, T0] if 0), spk_emb [B, cond_dim] fp32 device (the output of the caller's speaker encoder, models.py:213),
+ * wav [B, 1, T0*prod(rates)].  The 1x1 convs `cond_layer` / `conds.{i}` (tensor names "cond_layer.weight|bias",
+ * "conds.<i>.weight|bias") are evaluated per utterance and folded into the bias of conv_pre / ups[i]. */
+int bvg_vocoder_fwd_cond(bvg_vocoder* v, const float* latent, const float* spk_emb, float* wav, int B, int T0,
+                         bvg_stream_t stream);
 /* Host buffers: H2D, forward, D2H on `stream`, then waits for completion.
  * wav_dtype: 0 = fp32 wav in [-1,1]; 1 = int16 `clamp(32767*wav, -32767, 32767)` (infer_v2.py:740). */
 int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, int wav_dtype,

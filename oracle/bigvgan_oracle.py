@@ -21,6 +21,8 @@ What each function follows (paths relative to the reference root):
   conv1d / conv_transpose1d   torch.nn.Conv1d / ConvTranspose1d as built at bigvgan.py:59-66,76-83,285-287,306-312,348-350
   amp_block1             indextts/s2mel/modules/bigvgan/bigvgan.py:132-141
   generator_forward      indextts/s2mel/modules/bigvgan/bigvgan.py:360-386
+  generator_v1_forward   indextts/BigVGAN/models.py:212-250 (the IndexTTS-v1 speaker-conditioned generator, downstream of
+                         its ECAPA speaker encoder: the embedding is an input)
   fold_weight_norm       torch.nn.utils.weight_norm semantics used at bigvgan.py:388-400
 
 The FIR stages are written in their closed polyphase form with explicit index
@@ -231,6 +233,62 @@ def generator_forward(sd, h, mel, dtype=None, taps=None):
     if h.get("use_tanh_at_final", True):
         return torch.tanh(x)
     return x.clamp(-1.0, 1.0)
+
+
+def conv_transpose1d_taps(x, w, b, stride):
+    """General 3-tap polyphase statement of ConvTranspose1d(k, stride=u, pad=(k-u)/2), k-u even, pad <= u:
+    out[u*m + r] = sum_{tap in 0..2} W[:, :, r + pad + u*(1 - tap)]^T x[m + tap - 1]  (index in [0, k), x zero outside).
+    Used by the tests to pin the packing of the v1 plan (k = u and k = 2u layers)."""
+    B, Cin, T = x.shape
+    u = stride
+    k = w.shape[-1]
+    pad = (k - u) // 2
+    assert (k - u) % 2 == 0 and 0 <= pad <= u
+    wd = w.to(x.dtype)
+    xp = F.pad(x, (1, 1))
+    out = torch.zeros(B, w.shape[1], T, u, dtype=x.dtype)
+    for r in range(u):
+        for tap in range(3):
+            j = r + pad + u * (1 - tap)
+            if 0 <= j < k:
+                out[..., r] += torch.einsum("co,bct->bot", wd[:, :, j], xp[:, :, tap:tap + T])
+    out = out.reshape(B, w.shape[1], T * u)
+    if b is not None:
+        out = out + b.to(x.dtype).view(1, -1, 1)
+    return out
+
+
+def generator_v1_forward(sd, h, latent, spk_emb, dtype=None):
+    """IndexTTS-v1 generator (indextts/BigVGAN/models.py:212-250) after its speaker encoder:
+    latent [B, T, gpt_dim] (feat_upsample = False: `x.transpose(1, 2)`, :220), spk_emb [B, E] (the `[B, 1, E]` output of
+    `self.speaker_encoder`, transposed to [B, E, 1] at :214) -> wav [B, 1, T*prod(upsample_rates)].
+      x = conv_pre(x) + cond_layer(e)                      :223-224
+      per stage: x = ups[i](x) (+ conds[i](e))             :228-234, then the mean of the AMP blocks :236-243
+      x = tanh(conv_post(activation_post(x)))              :246-248"""
+    if any(k.endswith(".weight_v") for k in sd):
+        sd = fold_weight_norm(sd)
+    if dtype is not None:
+        sd = {k: v.to(dtype) for k, v in sd.items()}
+        latent = latent.to(dtype)
+        spk_emb = spk_emb.to(dtype)
+    if h.get("feat_upsample", False):
+        raise NotImplementedError("feat_upsample=True (4x linear interpolation of the latent) is not on the shipped v1 path")
+    nk = len(h["resblock_kernel_sizes"])
+    e = spk_emb.unsqueeze(-1)                                         # [B, E, 1]
+    x = conv1d(latent.transpose(1, 2), sd["conv_pre.weight"], sd["conv_pre.bias"])
+    x = x + conv1d(e, sd["cond_layer.weight"], sd["cond_layer.bias"])
+    for i, u in enumerate(h["upsample_rates"]):
+        x = conv_transpose1d(x, sd["ups.%d.0.weight" % i], sd["ups.%d.0.bias" % i], u)
+        if h.get("cond_d_vector_in_each_upsampling_layer", False):
+            x = x + conv1d(e, sd["conds.%d.weight" % i], sd["conds.%d.bias" % i])
+        xs = None
+        for j in range(nk):
+            y = amp_block1(sd, "resblocks.%d" % (i * nk + j), x, h, h["resblock_dilation_sizes"][j])
+            xs = y if xs is None else xs + y
+        x = xs / nk
+    x = _act(sd, "activation_post", x, h)
+    x = conv1d(x, sd["conv_post.weight"], sd.get("conv_post.bias"))
+    return torch.tanh(x)
 
 
 def snr_db(ref, test):

@@ -154,14 +154,61 @@ def gen_generators(mod):
     np.savez_compressed(os.path.join(OUT, "generators.npz"), **out)
 
 
+def gen_v1():
+    """IndexTTS-v1 speaker-conditioned generator (indextts/BigVGAN/models.py:130-250), UNMODIFIED forward
+    `m(latent, mel_ref)` including its randomly initialised ECAPA-TDNN speaker encoder; the embedding the encoder produced
+    is stored next to the waveform because the B200 path takes it as an input (the encoder is out of scope)."""
+    from indextts.BigVGAN import models as v1
+    out = {}
+    cases = [
+        ("v1_tiny", config.tiny_v1_hparams(), 21, 2, 13),
+        ("v1_tiny_nocond_up", config.tiny_v1_hparams(cond_d_vector_in_each_upsampling_layer=False, upsample_rates=[4, 2, 2],
+                                                     upsample_kernel_sizes=[4, 2, 4]), 22, 1, 9),
+    ]
+    for name, h, seed, B, T in cases:
+        sd = synth.make_state_dict(h, seed=seed)
+        torch.manual_seed(seed)                      # the speaker encoder keeps its own random init
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = v1.BigVGAN(v1_attr(h))
+            m.remove_weight_norm()
+        res = m.load_state_dict(sd, strict=False)
+        assert not res.unexpected_keys and all(k.startswith("speaker_encoder.") for k in res.missing_keys), res
+        m.eval()
+        latent = synth.make_latent(B, T, h["gpt_dim"])
+        g = torch.Generator().manual_seed(seed)
+        mel_ref = torch.randn(B, 60, h["num_mels"], generator=g)          # [B, frames, num_mels] as infer.py:476 passes it
+        with torch.no_grad():
+            emb = m.speaker_encoder(mel_ref, None)                        # [B, 1, E]
+            wav, loss = m(latent, mel_ref)
+        assert loss is None
+        out[name + ".latent"] = latent.numpy()
+        out[name + ".emb"] = emb.reshape(B, -1).numpy()
+        out[name + ".wav"] = wav.numpy()
+        out[name + ".sd_fingerprint"] = sd_fingerprint(sd)
+        out[name + ".seed"] = np.array([seed])
+        print(name, tuple(latent.shape), "->", tuple(wav.shape), "absmax %.4f" % wav.abs().max())
+    np.savez_compressed(os.path.join(OUT, "generators_v1.npz"), **out)
+
+
+def v1_attr(h):
+    class H(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+    return H(dict(h))
+
+
 def main():
     assert refshim.available(), "reference tree not found"
     torch.set_num_threads(os.cpu_count())
     os.makedirs(OUT, exist_ok=True)
     mod = refshim.load()
-    gen_activation(mod)
-    gen_ampblock(mod)
-    gen_generators(mod)
+    only = sys.argv[1:]
+    if not only or "v2" in only:
+        gen_activation(mod)
+        gen_ampblock(mod)
+        gen_generators(mod)
+    if not only or "v1" in only:
+        gen_v1()
 
 
 if __name__ == "__main__":

@@ -59,6 +59,25 @@ def test_conv_transpose1d(ops, case, precision):
     assert (y - ref).abs().max() <= 1e-5 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("case", [(2, 48, 24, 33, 4, 4), (1, 192, 96, 130, 4, 4), (1, 32, 16, 40, 2, 2), (1, 24, 12, 21, 6, 2),
+                                  (1, 16, 16, 19, 5, 3)], ids=str)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_transpose1d_general_kernel(ops, case, precision):
+    """k != 2*stride (padding (k - stride)/2): the k == stride layers of the IndexTTS-v1 plan (upsample_rates [4,4,4,4,2,2],
+    kernel sizes [8,8,4,4,4,4], indextts/BigVGAN/models.py:154-161) and other 3-tap polyphase shapes"""
+    B, Cin, Cout, T, k, u = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, k, generator=g) / (Cin * 2) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    if precision == "bf16":
+        x, w = bf(x), bf(w)
+    ref = O.conv_transpose1d(x.double(), w.double(), b.double(), u)
+    y = ops.conv_transpose1d(x.to(DEV), w.to(DEV), b.to(DEV), u, precision, 0).cpu().double()
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+
+
 def test_conv1d_full_size_tcgen05(ops):
     """the largest real layer (768ch, k=11, d=5) at 16 x 10 s would be 1.7 TFLOP for the
     CPU oracle; check one utterance slice against the oracle and the rest through
@@ -131,7 +150,9 @@ def test_conv_errors(ops):
     with pytest.raises(RuntimeError):
         ops.conv1d(x, torch.zeros(4, 4, 3, device=DEV), torch.zeros(4, device=DEV), 1, "fp16", 0)
     with pytest.raises(RuntimeError):
-        ops.conv_transpose1d(x, torch.zeros(4, 2, 6, device=DEV), torch.zeros(2, device=DEV), 2, "fp32", 0)  # k != 2u
+        ops.conv_transpose1d(x, torch.zeros(4, 2, 5, device=DEV), torch.zeros(2, device=DEV), 2, "fp32", 0)  # k - u odd
+    with pytest.raises(RuntimeError):
+        ops.conv_transpose1d(x, torch.zeros(4, 2, 8, device=DEV), torch.zeros(2, device=DEV), 2, "fp32", 0)  # padding 3 > u: more than 3 taps
 
 
 ACT_CASES = [  # B, Cin, Cout, T, k, dil   (T chosen around the 240-output tiles / 30-row rounds of the fused kernel)

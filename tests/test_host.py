@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SYMBOLS.keys())
-    assert lib.bvg_abi_version() == 1
+    assert lib.bvg_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
@@ -75,6 +75,28 @@ def test_dropin_state_dict_layout(pkg, synth, cfg):
     assert all(torch.equal(f[k], sd[k]) for k in sd)
     with pytest.raises(ValueError):
         pkg.BigVGAN(cfg.tiny_hparams(resblock="2"))
+
+
+def test_v1_dropin_state_dict_layout(pkg, synth, cfg):
+    """`BigVGANv1` carries the reference's v1 key names (indextts/BigVGAN/models.py:149-209): the v2 keys plus
+    cond_layer.* / conds.{i}.*; an injected speaker encoder lives under speaker_encoder.* and is not sent to the native plan"""
+    h = cfg.tiny_v1_hparams()
+    enc = torch.nn.Linear(3, 2)
+    m = pkg.BigVGANv1(h, speaker_encoder=enc)
+    m.remove_weight_norm()
+    sd = synth.make_state_dict(h, 1)
+    keys = set(m.state_dict().keys())
+    assert {"speaker_encoder.weight", "speaker_encoder.bias"} <= keys
+    assert keys - {"speaker_encoder.weight", "speaker_encoder.bias"} == set(sd.keys())
+    assert {"cond_layer.weight", "conds.2.bias", "conv_post.bias"} <= set(sd.keys())
+    assert tuple(sd["conv_pre.weight"].shape) == (h["upsample_initial_channel"], h["gpt_dim"], 7)
+    assert tuple(sd["ups.1.0.weight"].shape) == (48, 24, 4)           # a k == stride stage
+    assert not any(k.startswith("speaker_encoder.") for k in m.folded_state_dict())
+    assert m._native_conditioning() == (1, h["speaker_embedding_dim"], 1)
+    with pytest.raises(ValueError):
+        pkg.BigVGANv1(cfg.tiny_hparams())                            # v2 hyper-parameters: no gpt_dim
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, h["gpt_dim"]), speaker_embedding=torch.zeros(1, h["speaker_embedding_dim"]))   # CPU tensor
 
 
 def test_shard_ranges_and_chunks():

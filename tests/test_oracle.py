@@ -137,3 +137,40 @@ def test_oracle_matches_live_reference(synth, cfg):
         ref = m(mel)
     assert (O.generator_forward(sd, h, mel) - ref).abs().max() < 2e-6
     assert set(m.state_dict().keys()) == set(sd.keys())
+
+
+# ---- IndexTTS-v1 speaker-conditioned generator ------------------------------------------
+V1_CASES = {
+    "v1_tiny": lambda cfg: cfg.tiny_v1_hparams(),
+    "v1_tiny_nocond_up": lambda cfg: cfg.tiny_v1_hparams(cond_d_vector_in_each_upsampling_layer=False,
+                                                         upsample_rates=[4, 2, 2], upsample_kernel_sizes=[4, 2, 4]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(V1_CASES))
+def test_v1_generator_vs_reference_golden(golden, synth, cfg, name):
+    """the unmodified `indextts.BigVGAN.models.BigVGAN.forward(latent, mel_ref)` (its own ECAPA encoder included) against
+    the oracle fed the embedding that encoder produced"""
+    g = golden("generators_v1")
+    h = V1_CASES[name](cfg)
+    sd = synth.make_state_dict(h, seed=int(g[name + ".seed"][0]))
+    assert np.allclose(sd_fingerprint(sd), g[name + ".sd_fingerprint"], rtol=1e-12)
+    latent, emb, ref = t(g[name + ".latent"]), t(g[name + ".emb"]), t(g[name + ".wav"])
+    assert np.array_equal(latent.numpy(), synth.make_latent(latent.shape[0], latent.shape[1], h["gpt_dim"]).numpy())
+    wav = O.generator_v1_forward(sd, h, latent, emb)
+    assert wav.shape == ref.shape
+    assert (wav - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+    wav64 = O.generator_v1_forward(sd, h, latent, emb, dtype=torch.float64)
+    assert (wav64.float() - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("k,u", [(8, 4), (4, 4), (4, 2), (2, 2), (16, 8), (6, 2), (3, 1), (5, 3)])
+def test_conv_transpose_3tap_polyphase_general(k, u):
+    """every (k, stride) the native packer accepts is a 3-tap conv over the input rows (layout.cu: pack_convtr_kernel)"""
+    g = torch.Generator().manual_seed(k * 100 + u)
+    x = torch.randn(2, 5, 9, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 3, k, generator=g, dtype=torch.float64)
+    b = torch.randn(3, generator=g, dtype=torch.float64)
+    ref = O.conv_transpose1d(x, w, b, u)
+    assert ref.shape[-1] == 9 * u
+    assert (O.conv_transpose1d_taps(x, w, b, u) - ref).abs().max() < 1e-12

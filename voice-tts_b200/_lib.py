@@ -24,6 +24,7 @@ class BvgConfig(ctypes.Structure):
         ("resblock_dilations", (ctypes.c_int * 4) * 4), ("snake_kind", ctypes.c_int),
         ("snake_logscale", ctypes.c_int), ("use_tanh_at_final", ctypes.c_int),
         ("use_bias_at_final", ctypes.c_int), ("mode", ctypes.c_int), ("device", ctypes.c_int),
+        ("input_channels_last", ctypes.c_int), ("cond_dim", ctypes.c_int), ("cond_each_up", ctypes.c_int),
     ]
 
 
@@ -49,6 +50,7 @@ SYMBOLS = {
     "bvg_finalize": (_i, [_vp]),
     "bvg_workspace_bytes": (_i64, [_vp, _i, _i]),
     "bvg_vocoder_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "bvg_vocoder_fwd_cond": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bvg_vocoder_fwd_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "bvg_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
     "bvg_last_forward_launches": (_i, [_vp]),
@@ -74,7 +76,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.bvg_abi_version() != 1:
+    if lib.bvg_abi_version() != 2:
         raise RuntimeError("libbvg_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -18,7 +18,7 @@ from torch.nn.utils import remove_weight_norm, weight_norm
 
 from . import _lib, ops
 from .activation1d import Activation1d, Snake, SnakeBeta
-from .config import AttrDict, load_hparams_from_json, total_upsample
+from .config import AttrDict, in_channels, load_hparams_from_json, total_upsample
 
 
 def get_padding(kernel_size, dilation=1):
@@ -91,7 +91,7 @@ class BigVGAN(nn.Module):
         self.num_kernels = len(h["resblock_kernel_sizes"])
         self.num_upsamples = len(h["upsample_rates"])
         c0 = h["upsample_initial_channel"]
-        self.conv_pre = weight_norm(Conv1d(h["num_mels"], c0, 7, 1, padding=3))
+        self.conv_pre = weight_norm(Conv1d(in_channels(h), c0, 7, 1, padding=3))
         self.ups = nn.ModuleList()
         for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
             self.ups.append(nn.ModuleList([
@@ -136,7 +136,7 @@ class BigVGAN(nn.Module):
         """state dict with weight norm folded (the keys `remove_weight_norm()` leaves)."""
         sd = {}
         for k, v in self.state_dict().items():
-            if k.endswith(".weight_g"):
+            if k.endswith(".weight_g") or k.startswith("speaker_encoder."):
                 continue
             if k.endswith(".weight_v"):
                 g = self.state_dict()[k[:-2] + "_g"]
@@ -150,7 +150,8 @@ class BigVGAN(nn.Module):
         h = self.h
         lib = _lib.load()
         cfg = _lib.BvgConfig()
-        cfg.num_mels = h["num_mels"]
+        cfg.num_mels = in_channels(h)
+        cfg.input_channels_last, cfg.cond_dim, cfg.cond_each_up = self._native_conditioning()
         cfg.upsample_initial_channel = h["upsample_initial_channel"]
         cfg.num_upsamples = self.num_upsamples
         if self.num_upsamples > 8 or self.num_kernels > 4:
@@ -187,7 +188,11 @@ class BigVGAN(nn.Module):
         except Exception:
             lib.bvg_destroy(handle)
             raise
-        self._hid = ops.register_handle(handle, h["num_mels"], total_upsample(h), cfg.device)
+        self._hid = ops.register_handle(handle, in_channels(h), total_upsample(h), cfg.device)
+
+    def _native_conditioning(self):
+        """(input_channels_last, cond_dim, cond_each_up) of the native plan; the v1 subclass overrides it."""
+        return 0, 0, 0
 
     # ---- reference API ----------------------------------------------------------------------------
     def forward(self, x):

@@ -25,6 +25,31 @@ BIGVGAN_V2_22KHZ_80BAND_256X = {
 }
 
 
+# The IndexTTS-v1 speaker-conditioned generator (indextts/BigVGAN/models.py:130-250).  Its hyper-parameters live in
+# `checkpoints/config.yaml` (section `bigvgan`), which the reference downloads at deploy time and does NOT ship in the
+# tree; these are the values of the published IndexTTS-1.x configuration (gpt_dim 1024 for v1.0, 1280 for v1.5; x1024
+# upsampling of the GPT latent to 24 kHz).  Two stages use kernel == stride (padding 0), which the v2 plan never does.
+INDEXTTS_V1_BIGVGAN = {
+    "resblock": "1",
+    "upsample_rates": [4, 4, 4, 4, 2, 2],
+    "upsample_kernel_sizes": [8, 8, 4, 4, 4, 4],
+    "upsample_initial_channel": 1536,
+    "resblock_kernel_sizes": [3, 7, 11],
+    "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+    "feat_upsample": False,
+    "speaker_embedding_dim": 512,
+    "cond_d_vector_in_each_upsampling_layer": True,
+    "gpt_dim": 1024,
+    "activation": "snakebeta",
+    "snake_logscale": True,
+    "use_tanh_at_final": True,      # models.py:248 `torch.tanh` unconditionally
+    "use_bias_at_final": True,      # models.py:192 conv_post keeps its bias
+    "num_mels": 100,                # width of the speaker encoder's reference mel, not of the generator input
+    "hop_size": 256,
+    "sampling_rate": 24000,
+}
+
+
 class AttrDict(dict):
     """dict whose keys are also attributes (h.num_mels and h["num_mels"])."""
 
@@ -54,6 +79,26 @@ def tiny_hparams(**overrides) -> AttrDict:
     return h
 
 
+def v1_hparams(**overrides) -> AttrDict:
+    h = AttrDict(json.loads(json.dumps(INDEXTTS_V1_BIGVGAN)))
+    h.update(overrides)
+    return h
+
+
+def tiny_v1_hparams(**overrides) -> AttrDict:
+    """Shrunken v1 generator: a k = 2u stage, a k = u stage and a k = 4/u = 2 stage, 3 kernel sizes x 3 dilations (the v1
+    AMPBlock1 hard-codes three dilations, models.py:24-34), conditioning in every upsampling layer."""
+    h = v1_hparams(upsample_initial_channel=96, gpt_dim=40, speaker_embedding_dim=24,
+                   upsample_rates=[4, 4, 2], upsample_kernel_sizes=[8, 4, 4])
+    h.update(overrides)
+    return h
+
+
+def in_channels(h):
+    """input channels of conv_pre: the GPT latent width for the v1 generator (models.py:149), else num_mels."""
+    return h["gpt_dim"] if h.get("gpt_dim") else h["num_mels"]
+
+
 def stage_channels(h):
     c0 = h["upsample_initial_channel"]
     return [c0 // (2 ** (i + 1)) for i in range(len(h["upsample_rates"]))]
@@ -69,7 +114,7 @@ def total_upsample(h):
 def macs_per_frame(h):
     """Dense-conv multiply-accumulates per mel frame."""
     c0 = h["upsample_initial_channel"]
-    macs = h["num_mels"] * c0 * 7
+    macs = in_channels(h) * c0 * 7
     t = 1
     cin = c0
     for u, ku in zip(h["upsample_rates"], h["upsample_kernel_sizes"]):

@@ -42,7 +42,7 @@ int vocoder_create(const bvg_config* cfg, bvg_vocoder** out);
 int vocoder_set_tensor(bvg_vocoder* v, const char* name, const float* data, int64_t numel, int is_device);
 int vocoder_finalize(bvg_vocoder* v);
 int64_t vocoder_workspace_bytes(const bvg_vocoder* v, int B, int T0);
-int vocoder_forward(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, int B, int T0, cudaStream_t st);
+int vocoder_forward(bvg_vocoder* v, const float* mel, const float* emb, void* wav, int wav_i16, int B, int T0, cudaStream_t st);
 int vocoder_forward_host(bvg_vocoder* v, const float* mel_host, void* wav_host, int wav_dtype, int B, int T0,
                          cudaStream_t st);
 
@@ -123,7 +123,7 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
   if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "dense layer: unknown mode %d", mode);
   if (B == 0 || T == 0) return BVG_OK;
   if (!dst || !src || !weight) BVG_FAIL(BVG_EINVAL, "dense layer: null pointer");
-  if (up > 0 && (k != 2 * up || up % 2)) BVG_FAIL(BVG_EINVAL, "convtr1d: needs even stride u and k == 2u");
+  if (up > 0 && !convtr_shape_ok(k, up)) BVG_FAIL(BVG_EINVAL, "convtr1d: needs k - stride even and 0 <= (k - stride)/2 <= stride (padding (k - stride)/2, T_out = stride*T)");
   if (up == 0 && (k % 2 != 1 || dil < 1)) BVG_FAIL(BVG_EINVAL, "conv1d: needs odd k and dilation >= 1");
   int rc = ensure_device_ok();
   if (rc) return rc;
@@ -165,7 +165,7 @@ static int dense_layer(float* dst, const float* src, const float* weight, const 
     cudaError_t e = cudaMemsetAsync(bp, 0, b_b, st);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; break; }
     if (up > 0) {
-      if ((rc = pack_convtr_weight(wp, dt, weight, Cin, Cout, up, Cout_p, Cout_r, Cin_p, st))) break;
+      if ((rc = pack_convtr_weight(wp, dt, weight, Cin, Cout, up, k, Cout_p, Cout_r, Cin_p, st))) break;
       if (bias)
         for (int r = 0; r < up && e == cudaSuccess; ++r)
           e = cudaMemcpyAsync(bp + (size_t)r * Cout_p, bias, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -279,7 +279,12 @@ int bvg_set_tensor(bvg_vocoder* v, const char* name, const float* data, int64_t 
 int bvg_finalize(bvg_vocoder* v) { return vocoder_finalize(v); }
 int64_t bvg_workspace_bytes(const bvg_vocoder* v, int B, int T0) { return vocoder_workspace_bytes(v, B, T0); }
 int bvg_vocoder_fwd(bvg_vocoder* v, const float* mel, float* wav, int B, int T0, bvg_stream_t stream) {
-  return vocoder_forward(v, mel, wav, 0, B, T0, (cudaStream_t)stream);
+  return vocoder_forward(v, mel, nullptr, wav, 0, B, T0, (cudaStream_t)stream);
+}
+int bvg_vocoder_fwd_cond(bvg_vocoder* v, const float* latent, const float* spk_emb, float* wav, int B, int T0,
+                         bvg_stream_t stream) {
+  if (!spk_emb) BVG_FAIL(BVG_EINVAL, "bvg_vocoder_fwd_cond: null speaker embedding");
+  return vocoder_forward(v, latent, spk_emb, wav, 0, B, T0, (cudaStream_t)stream);
 }
 int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, int wav_dtype, int B, int T0,
                          bvg_stream_t stream) {

@@ -11,6 +11,8 @@ struct ConvArgs {
   const void* in;      // [B, T, Cin_p]
   const void* w;       // Wp[k][Cout_r][Cin_p]
   const float* bias;   // [Cout_r] fp32 (zero in pad rows) or nullptr
+  int64_t bias_bs = 0; // elements between the bias rows of consecutive utterances (0: one bias for all; > 0: the per-utterance
+                       // bias of the speaker-conditioned generator, indextts/BigVGAN/models.py:224-234 `x + cond(speaker_embedding)`)
   void* out;           // [B, T, out_ld]; channels [0, Cout_n) are written
   const float* res;    // optional fp32 [B, T, out_ld]
   const float* accum;  // optional fp32 [B, T, out_ld]
@@ -46,8 +48,15 @@ int btc_to_bct(float* dst, const void* src, int in_dtype, int B, int C, int Cp, 
 int weight_replica_rows(int Cout_n, int Cout_r);
 int pack_conv_weight(void* wp, int dtype, const float* w, int Cout, int Cin, int k, int Cout_r, int Cin_p,
                      cudaStream_t st);
-int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int Cout_p, int Cout_r,
+int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int k, int Cout_p, int Cout_r,
                        int Cin_p, cudaStream_t st);
+// k - u even, 0 <= (k - u)/2 <= u: the layer is a 3-tap conv over the input rows (T_out = u * T_in)
+static inline bool convtr_shape_ok(int k, int u) { return u >= 1 && k >= u && (k - u) % 2 == 0 && (k - u) / 2 <= u && k <= 2 * u + (k - u) / 2; }
+// per-utterance bias rows: out[b][r*Cp + c] = bias[c] + cb[c] + sum_e Wc[c][e] * emb[b][e]  (r < rep; pad entries zero)
+int cond_bias_launch(float* out, int64_t out_bs, const float* bias, const float* Wc, const float* cb, const float* emb, int B,
+                     int E, int C, int Cp, int rep, cudaStream_t st);
+// [B, T, C] fp32 -> [B, T, Cp] (cast to out_dtype, zero pad channels)
+int btc_pad_cast(void* dst, int out_dtype, const float* src, int64_t rows, int C, int Cp, cudaStream_t st);
 int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, const float* w, float bias, int B,
                      int Cp, int64_t T, int use_tanh, cudaStream_t st);
 int f32_to_i16(int16_t* dst, const float* src, int64_t n, cudaStream_t st);

@@ -80,7 +80,7 @@ conv_simt_kernel(ConvArgs a) {
       const int co = co0 + tx * 4 + jj;
       if (co >= a.Cout_n) continue;
       float v = acc[i][jj];
-      if (a.bias) v += a.bias[co];
+      if (a.bias) v += BVG_LDG(a.bias + (int64_t)b * a.bias_bs + co);
       if (a.res) v += BVG_LDG(a.res + rowoff + co);
       v *= a.scale;
       if (a.accum) v += BVG_LDG(a.accum + rowoff + co);

@@ -404,6 +404,7 @@ int umma_sm_count() {
 
 static bool conv_umma1_supported(const ConvArgs& a) {
   if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16) return false;
+  if (a.bias_bs != 0) return false;   // per-utterance bias: second-generation kernel only
   if (a.Cin_p % 16 != 0 || a.Cout_r % UM_M != 0) return false;
   if (a.T <= 0 || a.T > 0x7fffffffLL / 2) return false;
   if ((a.k - 1) * a.dil > 64) return false;  // activation-tile halo budget (UM_MAX_X_ROWS)

@@ -59,6 +59,7 @@ static_assert(U2_SMEM_USED <= U2_SMEM_BYTES, "shared-memory plan exceeds the opt
 
 struct U2Params {
   const float* bias;
+  int64_t bias_bs;   // per-utterance bias stride (0: shared)
   float scale;
   int B, T;
   int Cin_p, nchunks;
@@ -331,7 +332,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     uint32_t acc = 0, accph = 0, cb = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const U2Tile t = u2_tile(p, tile);
-      const float bv = (p.bias && lane_ok) ? __ldg(p.bias + t.cot * CW + ch) : 0.f;
+      const float bv = (p.bias && lane_ok) ? BVG_LDG(p.bias + (int64_t)t.b * p.bias_bs + t.cot * CW + ch) : 0.f;
 
       u2_wait(&t_full[acc], accph, dbg, w0);
       tc_fence_after();
@@ -414,7 +415,7 @@ static bool u2_plan(const ConvArgs& a, U2Params& p) {
   if (a.accum) al |= reinterpret_cast<uintptr_t>(a.accum);
   if (al & 15) return false;
 
-  p.bias = a.bias; p.scale = a.scale;
+  p.bias = a.bias; p.bias_bs = a.bias_bs; p.scale = a.scale;
   p.B = a.B; p.T = (int)a.T;
   p.Cin_p = a.Cin_p; p.nchunks = (int)ceil_div(a.Cin_p, 64);
   p.k = a.k; p.dil = a.dil; p.center = (a.k - 1) / 2;

@@ -492,7 +492,7 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
 // ------------------------------------------------------------------ host side ----
 static bool ua_plan(const ConvArgs& a, UAParams& p) {
-  if (a.accum || a.scale != 1.f) return false;
+  if (a.accum || a.scale != 1.f || a.bias_bs != 0) return false;
   if (a.in_dtype != BVG_BF16 || a.w_dtype != BVG_BF16 || a.out_dtype != BVG_BF16) return false;
   if (a.Cin_p % 8 != 0 || a.Cout_r % 128 != 0 || a.Cout_n <= 0 || a.Cout_n % 8 != 0) return false;
   if (a.T <= 0 || a.T > 0x3fffffffLL || a.B <= 0) return false;

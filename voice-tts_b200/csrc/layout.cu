@@ -5,7 +5,7 @@
 // Wp[tap][Cout_r][Cin_p] (input channel fastest), Cout_r = Cout padded to a
 // multiple of 128 - this is directly the K-major A operand of the tcgen05 kernel
 // and is also what the fp32 SIMT kernel reads.
-#include "common.cuh"
+#include "conv.cuh"
 
 namespace bvg {
 
@@ -96,16 +96,17 @@ __global__ void pack_conv_kernel(Tout* __restrict__ wp, const float* __restrict_
   }
 }
 
-// ConvTranspose1d weight [Cin, Cout, 2u] (stride u, padding u/2) -> a 3-tap conv over
+// ConvTranspose1d weight [Cin, Cout, k] (stride u, padding p = (k - u)/2, so T_out = u * T_in) -> a 3-tap conv over
 // the INPUT time axis producing u*Cout_p "phase channels" per input sample:
 //   out[u*m + r, co] = sum_{tap in 0..2} Wp[tap][r*Cout_p + co][:] . x[m + tap - 1, :]
-// with, for s = r + u/2:  s <  u : tap1 <- W[:,:,s],   tap0 <- W[:,:,s+u]
-//                         s >= u : tap2 <- W[:,:,s-u], tap1 <- W[:,:,s]
-// (polyphase form of torch ConvTranspose1d)
+// torch: out[t] = sum_{m', j : u*m' + j - p = t} W[:, :, j]^T x[m'], i.e. for t = u*m + r and input row m' = m + tap - 1
+// the weight index is j = r + p + u*(1 - tap) when it lies in [0, k).  k = 2u, p = u/2 is the BigVGAN v2 plan
+// (bigvgan.py:306-312; SURVEY.md 8(a) polyphase form); k = u, p = 0 (taps 0 and 2 all zero) appears in the v1
+// generator's plan (indextts/BigVGAN/models.py:154-161 with the published upsample_kernel_sizes).
 template <typename Tout>
-__global__ void pack_convtr_kernel(Tout* __restrict__ wp, const float* __restrict__ w, int Cin, int Cout, int u,
+__global__ void pack_convtr_kernel(Tout* __restrict__ wp, const float* __restrict__ w, int Cin, int Cout, int u, int k,
                                    int Cout_p, int Cout_r, int Cin_p, int rep_lr) {
-  const int k = 2 * u;
+  const int pad = (k - u) / 2;
   const int64_t n = (int64_t)3 * Cout_r * Cin_p;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin_p);
@@ -115,16 +116,8 @@ __global__ void pack_convtr_kernel(Tout* __restrict__ wp, const float* __restric
     float v = 0.f;
     const int r = vc / Cout_p, co = vc % Cout_p;
     if (ci < Cin && r < u && co < Cout) {
-      const int s = r + u / 2;
-      int widx = -1;
-      if (s < u) {
-        if (tap == 1) widx = s;
-        if (tap == 0) widx = s + u;
-      } else {
-        if (tap == 2) widx = s - u;
-        if (tap == 1) widx = s;
-      }
-      if (widx >= 0) v = w[((int64_t)ci * Cout + co) * k + widx];
+      const int widx = r + pad + u * (1 - tap);
+      if (widx >= 0 && widx < k) v = w[((int64_t)ci * Cout + co) * k + widx];
     }
     wp[i] = from_f32<Tout>(v);
   }
@@ -151,16 +144,17 @@ int pack_conv_weight(void* wp, int dtype, const float* w, int Cout, int Cin, int
   BVG_LAUNCHED();
   return BVG_OK;
 }
-int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int Cout_p, int Cout_r,
+int pack_convtr_weight(void* wp, int dtype, const float* w, int Cin, int Cout, int u, int k, int Cout_p, int Cout_r,
                        int Cin_p, cudaStream_t st) {
+  if (!convtr_shape_ok(k, u)) BVG_FAIL(BVG_EINVAL, "ConvTranspose1d: kernel %d / stride %d is not a 3-tap polyphase layer", k, u);
   const int rep_lr = weight_replica_rows(u * Cout_p, Cout_r);
   const int64_t n = (int64_t)3 * Cout_r * Cin_p;
   const int blocks = (int)(ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096);
   if (dtype == BVG_BF16)
-    pack_convtr_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)wp, w, Cin, Cout, u, Cout_p, Cout_r,
+    pack_convtr_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)wp, w, Cin, Cout, u, k, Cout_p, Cout_r,
                                                               Cin_p, rep_lr);
   else
-    pack_convtr_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cin, Cout, u, Cout_p, Cout_r, Cin_p, rep_lr);
+    pack_convtr_kernel<float><<<blocks, 256, 0, st>>>((float*)wp, w, Cin, Cout, u, k, Cout_p, Cout_r, Cin_p, rep_lr);
   BVG_LAUNCHED();
   return BVG_OK;
 }
@@ -327,6 +321,55 @@ int f32_to_i16(int16_t* dst, const float* src, int64_t n, cudaStream_t st) {
   if (n <= 0) return BVG_OK;
   const int blocks = (int)(ceil_div(n, 256) < 2048 ? ceil_div(n, 256) : 2048);
   f32_to_i16_kernel<<<blocks, 256, 0, st>>>(dst, src, n);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+// ---- speaker-conditioned generator (indextts/BigVGAN/models.py:224-234) -------------------------------------------
+// `x = conv_pre(x) + cond_layer(e)` and `x = ups[i](x) + conds[i](e)`: the 1x1 convs act on a length-1 sequence, so each is
+// a per-utterance vector that joins the layer's bias.  One warp per (utterance, channel): dot over the embedding, written
+// to all `rep` phase-channel copies of a ConvTranspose layer.  out rows are pre-zeroed in their pad entries by the caller.
+__global__ void cond_bias_kernel(float* __restrict__ out, int64_t out_bs, const float* __restrict__ bias,
+                                 const float* __restrict__ Wc, const float* __restrict__ cb, const float* __restrict__ emb,
+                                 int E, int C, int Cp, int rep) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int e = lane; e < E; e += 32) acc = fmaf(Wc[(int64_t)c * E + e], BVG_LDG(emb + (int64_t)b * E + e), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float v = (bias ? bias[c] : 0.f) + (acc + (cb ? cb[c] : 0.f));
+    for (int r = 0; r < rep; ++r) out[(int64_t)b * out_bs + (int64_t)r * Cp + c] = v;
+  }
+}
+int cond_bias_launch(float* out, int64_t out_bs, const float* bias, const float* Wc, const float* cb, const float* emb, int B,
+                     int E, int C, int Cp, int rep, cudaStream_t st) {
+  if (B <= 0 || C <= 0) return BVG_OK;
+  dim3 grid((unsigned)ceil_div(C, 8), (unsigned)B);
+  cond_bias_kernel<<<grid, 256, 0, st>>>(out, out_bs, bias, Wc, cb, emb, E, C, Cp, rep);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+// GPT latent [B, T, C] fp32 (models.py:220 `x.transpose(1, 2)`: already channels-last) -> conv_pre operand [B, T, Cp]
+template <typename Tout>
+__global__ void btc_pad_cast_kernel(Tout* __restrict__ dst, const float* __restrict__ src, int64_t rows, int C, int Cp) {
+  const int64_t n = rows * Cp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int64_t r = i / Cp;
+    dst[i] = from_f32<Tout>(c < C ? src[r * C + c] : 0.f);
+  }
+}
+int btc_pad_cast(void* dst, int out_dtype, const float* src, int64_t rows, int C, int Cp, cudaStream_t st) {
+  if (rows <= 0) return BVG_OK;
+  const int64_t n = rows * Cp;
+  const int blocks = (int)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
+  if (out_dtype == BVG_BF16) btc_pad_cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)dst, src, rows, C, Cp);
+  else btc_pad_cast_kernel<float><<<blocks, 256, 0, st>>>((float*)dst, src, rows, C, Cp);
   BVG_LAUNCHED();
   return BVG_OK;
 }

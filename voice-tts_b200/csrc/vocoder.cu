@@ -31,6 +31,14 @@ struct ConvW {
   bool has_w = false, has_b = false, want_b = true;
 };
 
+// 1x1 conv on the speaker embedding (models.py:204-209): weight [C][E] fp32, bias [C]
+struct CondW {
+  float* w = nullptr;
+  float* b = nullptr;
+  int C = 0;
+  bool has_w = false, has_b = false;
+};
+
 struct ActW {
   float* alpha = nullptr;  // [Cp] log scale
   float* beta = nullptr;   // [Cp] log scale
@@ -55,6 +63,9 @@ struct bvg_vocoder {
   std::vector<ConvW> convs1, convs2;   // [(stage*nk + j)*nd + l]
   std::vector<ActW> acts;              // [(stage*nk + j)*2*nd + a]
   ActW act_post;
+  CondW cond_pre;                      // cond_layer (added after conv_pre)
+  std::vector<CondW> conds;            // conds.{i} (added after ups[i]); empty unless cond_each_up
+  int E = 0;                           // speaker-embedding width (0: unconditioned v2 generator)
   float* post_w = nullptr;             // [7][Cp_last]
   float post_bias = 0.f;
   bool has_post_w = false, has_post_b = false;
@@ -131,6 +142,7 @@ static int alloc_act(ActW& a, int C, int gran) {
 
 // a1 / m / a2 / y exist once per concurrently running AMP block (nb sets)
 struct Buffers {
+  float *cb_pre, *cb_up[8];            // per-utterance bias rows of conv_pre / ups[i] (conditioned generator only)
   void *mel, *p0, *nx, *a1[4], *m[4], *a2[4];
   float *x, *y[4], *y2[4], *xs;   // y / y2: the residual stream of a block ping-pongs (fused conv2 reads halo rows of its input)
   int nb;
@@ -156,6 +168,12 @@ static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
   }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  size_t o_cb_pre = 0, o_cb_up[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (v->E > 0) {
+    o_cb_pre = take((size_t)B * v->conv_pre.Cout_r * 4);
+    if (!v->conds.empty())
+      for (int i = 0; i < v->nst; ++i) o_cb_up[i] = take((size_t)B * v->ups[i].Cout_r * 4);
+  }
   const size_t o_mel = take((size_t)B * T0 * v->mel_p * es);
   const size_t o_p0 = take((size_t)B * T0 * v->Cp[0] * es);
   const size_t o_nx = take(nmax * es);
@@ -172,6 +190,8 @@ static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
   }
   if (out) {
     unsigned char* base = (unsigned char*)v->arena;
+    out->cb_pre = (float*)(base + o_cb_pre);
+    for (int i = 0; i < 8; ++i) out->cb_up[i] = (float*)(base + o_cb_up[i]);
     out->mel = base + o_mel; out->p0 = base + o_p0; out->nx = base + o_nx;
     out->x = (float*)(base + o_x); out->xs = (float*)(base + o_xs);
     out->nb = nb;
@@ -224,9 +244,11 @@ struct ProfScope {
 static inline void prof_break(bvg_vocoder* v) { v->prof_last = -1; }
 
 static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, void* out, int out_dt,
-                    const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st) {
+                    const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st,
+                    const float* bias_rows = nullptr) {
   ConvArgs a;
   a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = res; a.accum = accum; a.scale = scale;
+  if (bias_rows) { a.bias = bias_rows; a.bias_bs = c.Cout_r; }   // per-utterance rows: layer bias + cond(speaker_embedding)
   a.in_dtype = in_dt; a.w_dtype = v->act_dt; a.out_dtype = out_dt;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
   a.k = c.k; a.dil = c.dil;
@@ -331,13 +353,15 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
   const int nb = bf.nb;
   int rc = BVG_OK;
   if (nb > 1 && (rc = ensure_streams(v))) return rc;
-  rc = run_conv(v, v->conv_pre, bf.mel, adt, bf.p0, adt, nullptr, nullptr, 1.f, B, T0, st);
+  const bool cond = v->E > 0;
+  rc = run_conv(v, v->conv_pre, bf.mel, adt, bf.p0, adt, nullptr, nullptr, 1.f, B, T0, st, cond ? bf.cb_pre : nullptr);
   if (rc) return rc;
   const void* stage_in = bf.p0;
   int64_t T = T0;
   for (int i = 0; i < v->nst; ++i) {
     // ConvTranspose1d: 3-tap conv over the input rows writing u*Cp phase channels == [B, u*T, Cp]
-    rc = run_conv(v, v->ups[i], stage_in, adt, bf.x, BVG_F32, nullptr, nullptr, 1.f, B, T, st);
+    rc = run_conv(v, v->ups[i], stage_in, adt, bf.x, BVG_F32, nullptr, nullptr, 1.f, B, T, st,
+                  (cond && !v->conds.empty()) ? bf.cb_up[i] : nullptr);
     if (rc) return rc;
     T *= v->cfg.upsample_rates[i];
     const bool last_stage = (i == v->nst - 1);
@@ -393,16 +417,32 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
   return run_act(v, v->act_post, bf.xs, BVG_F32, bf.a1[0], adt, B, T, st);
 }
 
-static int forward_chunk(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, int B, int T0,
+static int forward_chunk(bvg_vocoder* v, const float* mel, const float* emb, void* wav, int wav_i16, int B, int T0,
                          cudaStream_t st) {
   Buffers bf;
   plan_buffers(v, B, T0, &bf);
   int rc;
   {
     ProfScope ps(v, st, CAT_OTHER, 0.0);
-    rc = bct_to_btc(bf.mel, v->act_dt, mel, B, v->cfg.num_mels, v->mel_p, T0, st);
+    rc = v->cfg.input_channels_last ? btc_pad_cast(bf.mel, v->act_dt, mel, (int64_t)B * T0, v->cfg.num_mels, v->mel_p, st)
+                                    : bct_to_btc(bf.mel, v->act_dt, mel, B, v->cfg.num_mels, v->mel_p, T0, st);
   }
   if (rc) return rc;
+  if (v->E > 0) {
+    // per-utterance bias rows = layer bias + cond(speaker_embedding)  (models.py:224 `x + self.cond_layer(e)`, :233-234)
+    prof_break(v);
+    const ConvW& cp = v->conv_pre;
+    BVG_CUDA(cudaMemsetAsync(bf.cb_pre, 0, (size_t)B * cp.Cout_r * 4, st));
+    rc = cond_bias_launch(bf.cb_pre, cp.Cout_r, cp.bias, v->cond_pre.w, v->cond_pre.b, emb, B, v->E, cp.Cout, cp.Cout_p, 1, st);
+    if (rc) return rc;
+    for (size_t i = 0; i < v->conds.size(); ++i) {
+      const ConvW& cu = v->ups[i];
+      BVG_CUDA(cudaMemsetAsync(bf.cb_up[i], 0, (size_t)B * cu.Cout_r * 4, st));
+      rc = cond_bias_launch(bf.cb_up[i], cu.Cout_r, cu.bias, v->conds[i].w, v->conds[i].b, emb, B, v->E, cu.Cout, cu.Cout_p,
+                            cu.up, st);
+      if (rc) return rc;
+    }
+  }
   if (v->opt_graph && !v->opt_profile) {
     auto key = std::make_pair(B, T0);
     auto it = v->graphs.find(key);
@@ -452,8 +492,11 @@ static int ensure_arena(bvg_vocoder* v, size_t need) {
   return BVG_OK;
 }
 
-int vocoder_forward(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, int B, int T0, cudaStream_t st) {
+int vocoder_forward(bvg_vocoder* v, const float* mel, const float* emb, void* wav, int wav_i16, int B, int T0,
+                    cudaStream_t st) {
   if (!v || !v->finalized) BVG_FAIL(BVG_ESTATE, "vocoder handle is not finalized");
+  if (v->E > 0 && !emb) BVG_FAIL(BVG_EINVAL, "speaker-conditioned generator: call bvg_vocoder_fwd_cond with the speaker embedding");
+  if (v->E == 0 && emb) BVG_FAIL(BVG_EINVAL, "this generator takes no speaker embedding (cond_dim = 0)");
   if (B < 0 || T0 < 0) BVG_FAIL(BVG_EINVAL, "negative batch or length");
   if (B == 0 || T0 == 0) return BVG_OK;
   if (!mel || !wav) BVG_FAIL(BVG_EINVAL, "null mel/wav pointer");
@@ -470,7 +513,8 @@ int vocoder_forward(bvg_vocoder* v, const float* mel, void* wav, int wav_i16, in
   for (int b0 = 0; b0 < B; b0 += mb) {
     const int bc = (B - b0 < mb) ? B - b0 : mb;
     void* wv = wav_i16 ? (void*)((int16_t*)wav + (int64_t)b0 * Tw) : (void*)((float*)wav + (int64_t)b0 * Tw);
-    rc = forward_chunk(v, mel + (int64_t)b0 * v->cfg.num_mels * T0, wv, wav_i16, bc, T0, st);
+    rc = forward_chunk(v, mel + (int64_t)b0 * v->cfg.num_mels * T0, emb ? emb + (int64_t)b0 * v->E : nullptr, wv, wav_i16, bc,
+                       T0, st);
     if (rc) return rc;
   }
   v->last_launches = (int)(g_launches.load() - l0);
@@ -497,7 +541,7 @@ static int set_conv_tensor(bvg_vocoder* v, ConvW& c, bool is_weight, const float
   if (is_weight) {
     const int64_t want = (int64_t)c.Cin * c.Cout * c.k_torch;
     if (numel != want) BVG_FAIL(BVG_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)want, (long long)numel);
-    int rc = c.up > 0 ? pack_convtr_weight(c.w, v->act_dt, d_data, c.Cin, c.Cout, c.up, c.Cout_p, c.Cout_r, c.Cin_p, 0)
+    int rc = c.up > 0 ? pack_convtr_weight(c.w, v->act_dt, d_data, c.Cin, c.Cout, c.up, c.k_torch, c.Cout_p, c.Cout_r, c.Cin_p, 0)
                       : pack_conv_weight(c.w, v->act_dt, d_data, c.Cout, c.Cin, c.k, c.Cout_r, c.Cin_p, 0);
     if (rc) return rc;
     c.has_w = true;
@@ -593,6 +637,24 @@ int vocoder_set_tensor(bvg_vocoder* v, const char* name, const float* data, int6
     } else { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
   } else if (eat(s, "activation_post.")) {
     rc = set_act_tensor(v, v->act_post, s, d, numel, name);
+  } else if (v->E > 0 && (eat(s, "cond_layer.") || eat(s, "conds."))) {
+    CondW* cw = &v->cond_pre;
+    if (s[-2] == 's') {   // "conds.<i>."
+      if (!parse_int(s, &n) || n >= (int)v->conds.size() || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; cw = nullptr; }
+      else cw = &v->conds[n];
+    }
+    if (cw) {
+      const bool is_w = !strcmp(s, "weight");
+      if (!is_w && strcmp(s, "bias")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+      else if (numel != (is_w ? (int64_t)cw->C * v->E : (int64_t)cw->C)) {
+        set_error("%s: expected %lld elements, got %lld", name, (long long)(is_w ? (int64_t)cw->C * v->E : cw->C), (long long)numel);
+        rc = BVG_EINVAL;
+      } else {   // Conv1d(E, C, 1) weight [C, E, 1] is already the [C][E] matrix
+        cudaError_t e2 = cudaMemcpy(is_w ? cw->w : cw->b, d, numel * sizeof(float), cudaMemcpyDeviceToDevice);
+        if (e2 != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(e2)); rc = BVG_ECUDA; }
+        else (is_w ? cw->has_w : cw->has_b) = true;
+      }
+    }
   } else if (eat(s, "conv_post.")) {
     const int Cl = v->C[v->nst], Clp = v->Cp[v->nst];
     if (!strcmp(s, "weight")) {
@@ -633,10 +695,11 @@ int vocoder_create(const bvg_config* cfg, bvg_vocoder** out) {
       cfg->num_dilations < 1 || cfg->num_dilations > 4 || cfg->num_mels < 1 || cfg->upsample_initial_channel < 2)
     BVG_FAIL(BVG_EINVAL, "bvg_create: configuration out of range");
   if (cfg->mode != BVG_MODE_FP32 && cfg->mode != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_create: unknown mode %d", cfg->mode);
+  if (cfg->cond_dim < 0 || cfg->cond_dim > 65536) BVG_FAIL(BVG_EINVAL, "bvg_create: bad cond_dim %d", cfg->cond_dim);
   for (int i = 0; i < cfg->num_upsamples; ++i) {
     const int u = cfg->upsample_rates[i];
-    if (u < 2 || u % 2 != 0 || cfg->upsample_kernel_sizes[i] != 2 * u)
-      BVG_FAIL(BVG_EINVAL, "bvg_create: upsample stage %d needs even rate u and kernel 2u (got u=%d k=%d)", i, u,
+    if (!convtr_shape_ok(cfg->upsample_kernel_sizes[i], u))
+      BVG_FAIL(BVG_EINVAL, "bvg_create: upsample stage %d needs k - u even and 0 <= (k - u)/2 <= u (got u=%d k=%d)", i, u,
                cfg->upsample_kernel_sizes[i]);
     if ((cfg->upsample_initial_channel >> (i + 1)) < 1) BVG_FAIL(BVG_EINVAL, "bvg_create: too many stages for the channel count");
   }
@@ -686,6 +749,19 @@ int vocoder_create(const bvg_config* cfg, bvg_vocoder** out) {
       }
   TRY(alloc_act(v->act_post, v->C[v->nst], gran));
   TRY(dev_alloc((void**)&v->post_w, 7 * v->Cp[v->nst] * sizeof(float)));
+  v->E = cfg->cond_dim;
+  if (v->E > 0) {
+    auto alloc_cond = [&](CondW& c, int C) -> int {
+      c.C = C;
+      int r = dev_alloc((void**)&c.w, (size_t)C * v->E * sizeof(float));
+      return r ? r : dev_alloc((void**)&c.b, (size_t)C * sizeof(float));
+    };
+    TRY(alloc_cond(v->cond_pre, v->C[0]));
+    if (cfg->cond_each_up) {
+      v->conds.resize(v->nst);
+      for (int i = 0; i < v->nst; ++i) TRY(alloc_cond(v->conds[i], v->C[i + 1]));
+    }
+  }
 #undef TRY
   *out = v;
   return BVG_OK;
@@ -712,6 +788,11 @@ int vocoder_finalize(bvg_vocoder* v) {
   }
   for (size_t i = 0; i < v->acts.size(); ++i) if ((rc = chk_act(v->acts[i], "activations", (int)i))) return rc;
   if ((rc = chk_act(v->act_post, "activation_post", 0))) return rc;
+  if (v->E > 0) {
+    if (!v->cond_pre.has_w || !v->cond_pre.has_b) BVG_FAIL(BVG_ESTATE, "missing weight: cond_layer.{weight,bias}");
+    for (size_t i = 0; i < v->conds.size(); ++i)
+      if (!v->conds[i].has_w || !v->conds[i].has_b) BVG_FAIL(BVG_ESTATE, "missing weight: conds.%d.{weight,bias}", (int)i);
+  }
   if (!v->has_post_w) BVG_FAIL(BVG_ESTATE, "missing weight: conv_post.weight");
   if (v->cfg.use_bias_at_final && !v->has_post_b) BVG_FAIL(BVG_ESTATE, "missing weight: conv_post.bias");
   v->finalized = true;
@@ -729,6 +810,7 @@ int vocoder_forward_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
   if (B == 0 || T0 == 0) return BVG_OK;
   if (B < 0 || T0 < 0 || !mel_host || !wav_host) BVG_FAIL(BVG_EINVAL, "bad argument");
   if (wav_dtype != 0 && wav_dtype != 1) BVG_FAIL(BVG_EDTYPE, "wav_dtype must be 0 (fp32) or 1 (int16)");
+  if (v->E > 0) BVG_FAIL(BVG_EINVAL, "bvg_vocoder_fwd_host: speaker-conditioned generators go through bvg_vocoder_fwd_cond");
   BVG_CUDA(cudaSetDevice(v->cfg.device));
   const size_t mel_bytes = (size_t)B * v->cfg.num_mels * T0 * sizeof(float);
   const int64_t nw = (int64_t)B * T0 * v->total_up;
@@ -759,7 +841,7 @@ int vocoder_forward_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
   const bool mel_direct = is_pinned(mel_host), wav_direct = is_pinned(wav_host);
   if (!mel_direct) memcpy(v->pin_mel, mel_host, mel_bytes);
   BVG_CUDA(cudaMemcpyAsync(v->dev_mel, mel_direct ? mel_host : v->pin_mel, mel_bytes, cudaMemcpyHostToDevice, st));
-  int rc = vocoder_forward(v, v->dev_mel, v->dev_wav, wav_dtype, B, T0, st);
+  int rc = vocoder_forward(v, v->dev_mel, nullptr, v->dev_wav, wav_dtype, B, T0, st);
   if (rc) return rc;
   BVG_CUDA(cudaMemcpyAsync(wav_direct ? wav_host : v->pin_wav, v->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, st));
   BVG_CUDA(cudaStreamSynchronize(st));
@@ -782,6 +864,9 @@ extern "C" void bvg_destroy(bvg_vocoder* v) {
   for (auto& a : v->acts) free_act(a);
   free_act(v->act_post);
   if (v->post_w) cudaFree(v->post_w);
+  auto free_cond = [](CondW& c) { if (c.w) cudaFree(c.w); if (c.b) cudaFree(c.b); };
+  free_cond(v->cond_pre);
+  for (auto& c : v->conds) free_cond(c);
   for (auto& e : v->prof_ev) cudaEventDestroy(e);
   for (auto& e : v->ev_pool) cudaEventDestroy(e);
   for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);

@@ -283,3 +283,32 @@ def vocoder(mel: torch.Tensor, handle_id: int) -> torch.Tensor:
 def _(mel, handle_id):
     _, _, total_up, _ = _HANDLES[handle_id]
     return mel.new_empty(mel.shape[0], 1, mel.shape[2] * total_up)
+
+
+@torch.library.custom_op("bvg_b200::vocoder_cond", mutates_args=())
+def vocoder_cond(latent: torch.Tensor, spk_emb: torch.Tensor, handle_id: int) -> torch.Tensor:
+    """speaker-conditioned v1 generator (indextts/BigVGAN/models.py:212-250): latent [B, T, gpt_dim], spk_emb [B, E]."""
+    handle, cin, total_up, dev = _HANDLES[handle_id]
+    _require_cuda(latent, "latent")
+    _require_cuda(spk_emb, "spk_emb")
+    if latent.dim() != 3 or latent.shape[2] != cin:
+        raise RuntimeError("vocoder_cond expects latent [B, T, %d], got %s" % (cin, tuple(latent.shape)))
+    if latent.dtype != torch.float32 or spk_emb.dtype != torch.float32:
+        raise RuntimeError("vocoder_cond expects float32 tensors")
+    if spk_emb.dim() != 2 or spk_emb.shape[0] != latent.shape[0]:
+        raise RuntimeError("vocoder_cond expects spk_emb [B, E], got %s" % (tuple(spk_emb.shape),))
+    if latent.device.index != dev or spk_emb.device.index != dev:
+        raise RuntimeError("inputs are not on the vocoder handle's device cuda:%d" % dev)
+    B, T, _ = latent.shape
+    wav = torch.empty(B, 1, T * total_up, device=latent.device, dtype=torch.float32)
+    with torch.cuda.device(latent.device):
+        rc = _lib.load().bvg_vocoder_fwd_cond(handle, latent.data_ptr(), spk_emb.data_ptr(), wav.data_ptr(), B, T,
+                                              _stream(latent))
+    _lib.check(rc, "bvg_vocoder_fwd_cond")
+    return wav
+
+
+@vocoder_cond.register_fake
+def _(latent, spk_emb, handle_id):
+    _, _, total_up, _ = _HANDLES[handle_id]
+    return latent.new_empty(latent.shape[0], 1, latent.shape[1] * total_up)

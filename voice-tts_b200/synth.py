@@ -16,7 +16,7 @@ import zlib
 
 import torch
 
-from .config import stage_channels
+from .config import in_channels, stage_channels
 
 
 def _gen(seed, key):
@@ -68,8 +68,9 @@ def state_dict_spec(h):
     generator state dict, in the reference's naming."""
     spec = []
     c0 = h["upsample_initial_channel"]
-    spec.append(("conv_pre.weight", (c0, h["num_mels"], 7), "conv"))
-    spec.append(("conv_pre.bias", (c0,), "bias:%d" % (h["num_mels"] * 7)))
+    cin0 = in_channels(h)
+    spec.append(("conv_pre.weight", (c0, cin0, 7), "conv"))
+    spec.append(("conv_pre.bias", (c0,), "bias:%d" % (cin0 * 7)))
     cin = c0
     for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
         cout = cin // 2
@@ -101,6 +102,14 @@ def state_dict_spec(h):
     spec.append(("conv_post.weight", (1, chans[-1], 7), "conv"))
     if h.get("use_bias_at_final", True):
         spec.append(("conv_post.bias", (1,), "bias:%d" % (chans[-1] * 7)))
+    E = h.get("speaker_embedding_dim", 0)
+    if E:   # speaker-conditioned v1 generator (indextts/BigVGAN/models.py:204-209): 1x1 convs on the embedding
+        spec.append(("cond_layer.weight", (c0, E, 1), "conv"))
+        spec.append(("cond_layer.bias", (c0,), "bias:%d" % E))
+        if h.get("cond_d_vector_in_each_upsampling_layer", False):
+            for i, c in enumerate(chans):
+                spec.append(("conds.%d.weight" % i, (c, E, 1), "conv"))
+                spec.append(("conds.%d.bias" % i, (c,), "bias:%d" % E))
     return spec
 
 
@@ -133,4 +142,24 @@ def make_mel(batch, num_mels, frames, first_utterance=0):
         g = torch.Generator(device="cpu")
         g.manual_seed(1000 + first_utterance + b)
         out[b] = (torch.randn(num_mels, frames, generator=g) * 2.0 - 4.0).clamp_(-11.5, 2.0)
+    return out
+
+
+def make_latent(batch, frames, gpt_dim, first_utterance=0):
+    """Synthetic GPT latents for the v1 generator: N(0, 1) [B, T, gpt_dim], seed 2000+utterance."""
+    out = torch.empty(batch, frames, gpt_dim, dtype=torch.float32)
+    for b in range(batch):
+        g = torch.Generator(device="cpu")
+        g.manual_seed(2000 + first_utterance + b)
+        out[b] = torch.randn(frames, gpt_dim, generator=g)
+    return out
+
+
+def make_speaker_embedding(batch, dim, first_utterance=0):
+    """Synthetic speaker embeddings [B, dim] (stand-in for the ECAPA-TDNN output, models.py:213), seed 3000+utterance."""
+    out = torch.empty(batch, dim, dtype=torch.float32)
+    for b in range(batch):
+        g = torch.Generator(device="cpu")
+        g.manual_seed(3000 + first_utterance + b)
+        out[b] = torch.randn(dim, generator=g)
     return out
