@@ -197,7 +197,15 @@ def act_sweep(dev, pk):
     taps = O.kaiser_taps().tolist()
     rows = []
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    for dt, fast in ((torch.bfloat16, True), (torch.float32, False), (torch.float32, True)):
+    # GPU-side comparator: the reference's own fused kernel (anti_alias_activation_cuda.cu:43-246) rebuilt for sm_100a by
+    # oracle/build_ref_kernel.py - series "reference_kernel" (fast-math sin, log-scale alpha/beta like ours); absent -> skipped
+    from oracle import build_ref_kernel
+    refk = build_ref_kernel.load()
+    taps_t = O.kaiser_taps().to(dev)
+    series = [(torch.bfloat16, True, None), (torch.float32, False, None), (torch.float32, True, None)]
+    if refk is not None:
+        series += [(torch.bfloat16, True, refk), (torch.float32, True, refk)]
+    for dt, fast, rk in series:
         for C in (24, 48, 192, 768, 1536):
             for T in (8192, 131072, 2097152):
                 es = 2 if dt == torch.bfloat16 else 4
@@ -208,20 +216,28 @@ def act_sweep(dev, pk):
                 x = torch.randn(B, C, T, device=dev).to(dt)
                 a = torch.randn(C, device=dev) * 0.5
                 b = torch.randn(C, device=dev) * 0.5
+                if rk is not None:
+                    if B * C * T >= 2 ** 31:      # the reference kernel indexes with 32-bit ints (.cu:68)
+                        continue
+                    fdt, adt, bdt = taps_t.to(dt), a.to(dt), b.to(dt)   # the v2 copy reads filters / alpha / beta as input_t (.cu:47-50)
+                    run = lambda: rk.forward(x, fdt, fdt, adt, bdt)
+                else:
+                    run = lambda: ops.act1d(x, a, b, taps, taps, fast)
                 for _ in range(2):
-                    ops.act1d(x, a, b, taps, taps, fast)
+                    run()
                 ts = []
                 for _ in range(5):
                     flush.zero_()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    ops.act1d(x, a, b, taps, taps, fast)
+                    run()
                     e1.record()
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
                 ts.sort()
                 gbs = 2.0 * B * C * T * es / (ts[len(ts) // 2] * 1e-3) / 1e9
-                rows.append({"dtype": str(dt)[6:], "snake": "fast" if fast else "accurate", "B": B, "C": C, "T": T,
+                rows.append({"impl": "reference_kernel" if rk is not None else "ours",
+                             "dtype": str(dt)[6:], "snake": "fast" if fast else "accurate", "B": B, "C": C, "T": T,
                              "ms": ts[len(ts) // 2], "GBps": round(gbs, 1), "frac_hbm": round(gbs / pk["hbm_gbs"], 3)})
                 del x
     return rows

@@ -7,13 +7,13 @@
 //   1. the tile plus an 8-sample halo is staged in shared memory by ONE bulk
 //      async copy (cp.async.bulk / UBLKCP, mbarrier completion) when the row
 //      pitch is 16-byte aligned, else by cooperative scalar loads;
-//   2. the tile is cut into 256 odd-length segments (odd stride => conflict-free
-//      LDS/STS); thread i walks segments i and i+128 TOGETHER as one f32x2 pair
+//   2. the tile is cut into <= 256 odd-length segments (odd stride => conflict-free
+//      LDS/STS); a thread walks two segments TOGETHER as one f32x2 pair
 //      (FFMA2: two FMAs per issue slot - the kernel is FP32-issue bound, not HBM
 //      bound, see profiles/) with the rotating 6+12 register window: 24 FMA + 2
-//      snake per output, no recomputation inside a segment.  Segments that touch
-//      a row end (replicate clamps, v edge rules) or are short take the scalar
-//      generic routine;
+//      snake per output, no recomputation inside a segment.  The few outputs next
+//      to a row end (replicate clamps, v edge rules) are evaluated one per thread
+//      straight from the definition (bit-identical operation order);
 //   3. outputs are staged in shared memory and leave with ONE bulk async store
 //      (or cooperative stores on the unaligned path).
 #include "act_packed.cuh"
@@ -25,57 +25,34 @@ constexpr int kBctSegs = 2 * kBctThreads;   // segments per tile
 constexpr int kBctMaxSeg = 31;              // 6n-5
 constexpr int kBctHalo = 8;                 // >= 5, multiple of 8 elements => 16 B for bf16, 32 B for fp32
 
-// generic scalar segment [t0, t1): any position, any length
+// One output straight from the definition (clamped indices = the replicate rules of the torch operator), with the operation
+// order of the sliding-window routines: v[2tau+5] and v[2tau+6] are the "odd"/"even" results of window step tau
+//   v[2tau+5] = snake(init + sum_{q=0..5} up[2q]   * x[clamp(tau+5-q)])      (fma chain, q ascending)
+//   v[2tau+6] = snake(init + sum_{q=0..5} up[2q+1] * x[clamp(tau+5-q)])
+//   y[t]      = down[0]*v[c(2t-5)] then fma(down[k], v[c(2t-5+k)], .) for k = 1..11,   c(m) = clamp(m, 0, 2T-1)
 template <typename T, bool FAST>
-__device__ __forceinline__ void bct_segment_scalar(const T* s_in, T* s_out, const Taps& taps, float a, float ib,
-                                                   int64_t t0, int64_t t1, int64_t tile_t0, int64_t lo, int n_in,
+__device__ __forceinline__ float bct_output_direct(const T* s_in, const Taps& taps, float a, float ib, int64_t t, int64_t lo,
                                                    int64_t Tlen) {
-  const int64_t tlast = Tlen - 1;
-  float X[6], V[12], vend = 0.f;
+  const int64_t tlast = Tlen - 1, mlast = 2 * Tlen - 1;
+  float acc = 0.f;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    int64_t ti = t0 - 5 + i;
-    ti = ti < 0 ? 0 : (ti > tlast ? tlast : ti);
-    X[i] = to_f32<T>(s_in[ti - lo]);
-  }
-  const int nsteps = (int)(t1 - t0) + 5;
-  for (int base = 0; base < nsteps; base += 6) {
+  for (int k = 0; k < 12; ++k) {
+    int64_t m = 2 * t - 5 + k;
+    m = m < 0 ? 0 : (m > mlast ? mlast : m);
+    const int odd = (int)(m & 1);
+    const int64_t tau = odd ? (m - 5) / 2 : (m - 6) / 2;   // exact: m - 5 / m - 6 are even
+    float u = snake_acc_init<FAST>(ib);
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const int64_t t = t0 - 5 + base + s;
-      int64_t tl = t + 5;
-      tl = tl > tlast ? tlast : tl;
-      // past the end of the segment the index may leave the staged range; those steps
-      // produce nothing, so any in-range sample will do
-      int idx = (int)(tl - lo);
-      idx = idx < n_in ? idx : n_in - 1;
-      X[(s + 5) % 6] = to_f32<T>(s_in[idx]);
-      float uo = snake_acc_init<FAST>(ib), ue = uo;   // same operation order as the packed path
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float xv = X[(s + 5 - q) % 6];
-        uo = fmaf(taps.up[2 * q], xv, uo);
-        ue = fmaf(taps.up[2 * q + 1], xv, ue);
-      }
-      float vo = snake_apply<FAST>(uo, a, ib);
-      float ve = snake_apply<FAST>(ue, a, ib);
-      if (t >= Tlen - 3) {          // right edge: v[m >= 2T] := v[2T-1] (odd sample of step T-3)
-        if (t == Tlen - 3) vend = vo;
-        vo = vend;
-        ve = vend;
-      }
-      V[(2 * s + 10) % 12] = vo;
-      V[(2 * s + 11) % 12] = ve;
-      if (s == 2 && base == 0 && t0 == 0) {   // left edge: v[m < 0] := v[0]
-        const float v0 = V[3];
-        V[10] = v0; V[11] = v0; V[0] = v0; V[1] = v0; V[2] = v0;
-      }
-      float acc = taps.down[0] * V[(2 * s) % 12];
-#pragma unroll
-      for (int k = 1; k < 12; ++k) acc = fmaf(taps.down[k], V[(2 * s + k) % 12], acc);
-      if (t >= t0 && t < t1) s_out[t - tile_t0] = from_f32<T>(acc);
+    for (int q = 0; q < 6; ++q) {
+      int64_t xi = tau + 5 - q;
+      xi = xi < 0 ? 0 : (xi > tlast ? tlast : xi);
+      const float xv = to_f32<T>(s_in[xi - lo]);
+      u = fmaf(odd ? taps.up[2 * q] : taps.up[2 * q + 1], xv, u);
     }
+    const float v = snake_apply<FAST>(u, a, ib);
+    acc = k == 0 ? taps.down[0] * v : fmaf(taps.down[k], v, acc);
   }
+  return acc;
 }
 
 #define BVG_BCT2_STEP(S, WITH_DOWN, OIDX)                                                   \
@@ -144,13 +121,34 @@ act1d_bct_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __
 
   const int64_t tile_end = tile_t0 + tile_len < Tlen ? tile_t0 + tile_len : Tlen;
   const int64_t tlast = Tlen - 1;
-  const int64_t t0a = tile_t0 + (int64_t)threadIdx.x * L;
-  const int64_t t0b = t0a + (int64_t)kBctThreads * L;
-  const bool fast_a = t0a >= 5 && t0a + L + 4 <= tlast && t0a + L <= tile_end;
-  const bool fast_b = t0b >= 5 && t0b + L + 4 <= tlast && t0b + L <= tile_end;
+  // Work split of a tile.  FAST segments (full length L, no index clamp anywhere in their 5-step warm-up and run-out) are
+  // segments [s_first, s_tail) and are walked in pairs by the packed routine: thread i < H = ceil(nfast / 2) takes
+  // segments s_first + i and s_first + i + H (pairing at distance H, not at a fixed 128, keeps both halves of every pair
+  // full in a partly filled tile; an odd segment out is walked twice by its thread, which costs nothing extra because
+  // the rest of its warp is in the same loop).  SLOW outputs - the first segment of a row and the last one or two,
+  // where the replicate rules of the torch operator apply - are NOT walked: each of them (at most ~3 L per tile) is
+  // evaluated on its own by one thread, starting from the top of the block where threads are idle, straight from the
+  // definition with clamped indices and the SAME operation order as the sliding window, so the value is bit-identical.
+  // (Before: the scalar edge-aware walk of two segments cost as many warp instructions as the whole rest of the tile -
+  //  ncu, [43,192,8192] fp32: 154 M warp instructions for 68 M elements against 73 M for 76 M elements at T = 131072 -
+  //  because the warp holding an edge thread runs both paths one after the other, and with T = 8192 every tile has an edge.)
+  const int s_first = tile_t0 == 0 ? 1 : 0;
+  const int len = (int)(tile_end - tile_t0);         // 32-bit from here on: a 64-bit division costs ~100 instructions per thread
+  int s_tail = len / L;
+  {
+    const int64_t room64 = tlast - 4 - tile_t0;      // segments must also end 4 samples before the end of the row
+    const int room = room64 > (int64_t)len ? len : (room64 < 0 ? 0 : (int)room64);
+    const int s2 = room / L;
+    if (s2 < s_tail) s_tail = s2;
+  }
+  const int nfast = s_tail > s_first ? s_tail - s_first : 0;
+  const int H = (nfast + 1) >> 1;
 
-  if (fast_a && fast_b) {
-    // ---- both segments interior and full (L = 6n-5): packed pair, no clamps/predicates ----
+  if ((int)threadIdx.x < H) {
+    const int sa = s_first + (int)threadIdx.x;
+    int sb = sa + H;
+    if (sb >= s_tail) sb = sa;
+    const int64_t t0a = tile_t0 + (int64_t)sa * L, t0b = tile_t0 + (int64_t)sb * L;
     SnakePair<FAST> sn;
     sn.init(al, al, be, be);
     const T* ipa = s_in + (t0a - 5 - lo);
@@ -173,13 +171,21 @@ act1d_bct_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __
       for (int s = 0; s < 6; ++s) BVG_BCT2_STEP(s, true, s)
       ipa += 6; ipb += 6; opa += 6; opb += 6;
     }
-  } else {
-    const float a = expf(al);
-    const float ib = 1.0f / (expf(be) + 1e-9f);
-    int64_t t1a = t0a + L < tile_end ? t0a + L : tile_end;
-    int64_t t1b = t0b + L < tile_end ? t0b + L : tile_end;
-    if (t0a < t1a) bct_segment_scalar<T, FAST>(s_in, s_out, taps, a, ib, t0a, t1a, tile_t0, lo, n_in, Tlen);
-    if (t0b < t1b) bct_segment_scalar<T, FAST>(s_in, s_out, taps, a, ib, t0b, t1b, tile_t0, lo, n_in, Tlen);
+  }
+  {
+    const int64_t head_end = tile_t0 == 0 ? (L < tile_end ? L : tile_end) : tile_t0;
+    int64_t tail_start = tile_t0 + (int64_t)(s_tail > 0 ? s_tail : 0) * L;
+    if (tail_start < head_end) tail_start = head_end;
+    const int nhead = (int)(head_end - tile_t0);
+    const int nslow = nhead + (int)(tile_end - tail_start);
+    if (nslow > 0) {
+      const float a = expf(al);
+      const float ib = 1.0f / (expf(be) + 1e-9f);
+      for (int j = kBctThreads - 1 - (int)threadIdx.x; j < nslow; j += kBctThreads) {
+        const int64_t t = j < nhead ? tile_t0 + j : tail_start + (j - nhead);
+        s_out[t - tile_t0] = from_f32<T>(bct_output_direct<T, FAST>(s_in, taps, a, ib, t, lo, Tlen));
+      }
+    }
   }
 
   const int n_out = (int)(tile_end - tile_t0);
@@ -207,12 +213,14 @@ static int launch_bct(void* dst, const void* src, const float* alpha_log, const 
   // tiles: as few as possible per row, then the shortest 6n-5 segment that covers them
   const int max_tile = kBctSegs * kBctMaxSeg;
   const int tiles_per_row = (int)ceil_div(Tlen, max_tile);
-  const int64_t per_tile = ceil_div(Tlen, tiles_per_row);
+  // equal tiles (a multiple of 256 elements keeps every tile start 16-byte aligned for the bulk copies), cut into the
+  // shortest 6n-5 segments that cover one tile with at most 256 of them
+  const int64_t per_tile = ceil_div(ceil_div(Tlen, tiles_per_row), 256) * 256;
   int L = (int)ceil_div(per_tile, kBctSegs);
   L = (int)ceil_div(L + 5, 6) * 6 - 5;  // 6n-5: whole 6-step bodies; odd => conflict-free shared-memory walk
   if (L < 7) L = 7;                 // only the first segment of a row may see v[m<0] (needs 2*L-5 >= 0)
   if (L > kBctMaxSeg) L = kBctMaxSeg;
-  const int tile_len = kBctSegs * L;   // multiple of 256 elements
+  const int tile_len = (int)(per_tile < (int64_t)kBctSegs * L ? per_tile : (int64_t)kBctSegs * L);
   const int64_t blocks = rows * tiles_per_row;
   if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d: tensor too large (%lld blocks)", (long long)blocks);
   const int aligned = ((Tlen * (int64_t)sizeof(T)) % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) &&
