@@ -11,6 +11,7 @@ h = cfg.default_hparams(); sd = synth.make_state_dict(h, 1234)
 m = pkg.BigVGAN(h, precision="bf16")
 with contextlib.redirect_stdout(io.StringIO()): m.remove_weight_norm()
 m.load_state_dict(sd); m = m.to("cuda:0").eval(); m.set_option("profile", 1)
+m.set_option("streams", 1)   # per-launch event times only mean something on the serial schedule (override with BVG_OPTS=streams=3)
 for kv in os.environ.get("BVG_OPTS", "").split(","):   # e.g. BVG_OPTS=fuse_act=0,fuse_res=2
     if "=" in kv: m.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 mel = synth.make_mel(B, 80, T0).to("cuda:0")
