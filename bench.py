@@ -193,15 +193,17 @@ def act_sweep(dev, pk):
     accurate snake (the <= 1e-5 parity mode) and fp32 I/O with the fast snake (BVG_ACT_FAST_SIN)."""
     import torch
     ops = importlib.import_module("voice-tts_b200.ops")
-    from oracle import bigvgan_oracle as O
-    taps = O.kaiser_taps().tolist()
+    synth = importlib.import_module("voice-tts_b200.synth")
+    taps_cpu = synth.kaiser_sinc_filter1d().reshape(-1)
+    taps = taps_cpu.tolist()
     rows = []
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    # GPU-side comparator: the reference's own fused kernel (anti_alias_activation_cuda.cu:43-246) rebuilt for sm_100a by
-    # oracle/build_ref_kernel.py - series "reference_kernel" (fast-math sin, log-scale alpha/beta like ours); absent -> skipped
+    # GPU-side comparator (a reference measurement like `--impl reference`, never on the product path): the reference's own
+    # fused kernel (anti_alias_activation_cuda.cu:43-246) rebuilt for sm_100a by oracle/build_ref_kernel.py into oracle/_ref -
+    # series "reference_kernel" (fast-math sin, log-scale alpha/beta like ours); absent -> skipped
     from oracle import build_ref_kernel
     refk = build_ref_kernel.load()
-    taps_t = O.kaiser_taps().to(dev)
+    taps_t = taps_cpu.to(dev)
     series = [(torch.bfloat16, True, None), (torch.float32, False, None), (torch.float32, True, None)]
     if refk is not None:
         series += [(torch.bfloat16, True, refk), (torch.float32, True, refk)]
