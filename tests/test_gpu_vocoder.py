@@ -316,3 +316,37 @@ def test_other_configurations_vs_oracle(pkg, synth, cfg, overrides):
             snr = O.snr_db(ref, wav)
             print("%s bf16 SNR %.1f dB" % (overrides, snr))
             assert snr >= bar
+
+
+def test_full_generator_bf16x3_mode(pkg, golden, full_model_sd):
+    """precision="bf16x3": fp32 storage, every convolution as bf16 tensor-core passes over three-term splits of both
+    operands (vocoder.cu: run_conv_split; 3 term pairs by default, 6 / 9 by option).  Not the parity mode - the tensor
+    cores' fp32 accumulation is not round-to-nearest, so even the exact 9-term form stops at 1.8e-5 where the SIMT fp32
+    kernels reach 2.6e-6 - but far beyond the bf16 mode: >= 90 dB and <= 5e-5 of max-abs on the full generator."""
+    h, sd = full_model_sd
+    g = golden("generators")
+    ref = t(g["full.wav"])
+    m = make(pkg, h, sd, "bf16x3")
+    snrs = {}
+    for terms in (3, 6, 9):
+        m.set_option("split_terms", terms)
+        with torch.no_grad():
+            wav = m(t(g["full.mel"]).to(DEV)).cpu()
+        err = float((wav - ref).abs().max() / ref.abs().max())
+        snrs[terms] = O.snr_db(ref, wav)
+        print("full bf16x3, %d term pairs: rel err %.2e, SNR %.1f dB" % (terms, err, snrs[terms]))
+        assert snrs[terms] >= 90.0 and err <= 5e-5
+    assert snrs[6] >= snrs[3] - 0.5 and snrs[9] >= snrs[6] - 0.5
+
+
+def test_tiny_generator_bf16x3_mode_ragged(pkg, synth, cfg):
+    h = cfg.tiny_hparams()
+    sd = synth.make_state_dict(h, seed=7)
+    m = make(pkg, h, sd, "bf16x3")
+    for B, T in ((2, 21), (1, 1), (3, 40)):
+        mel = synth.make_mel(B, h["num_mels"], T)
+        ref = O.generator_forward(sd, h, mel)
+        with torch.no_grad():
+            wav = m(mel.to(DEV)).cpu()
+        assert wav.shape == ref.shape
+        assert O.snr_db(ref, wav) >= 75.0, (B, T)

@@ -83,8 +83,12 @@ class BigVGAN(nn.Module):
         self.h = h
         self.h["use_cuda_kernel"] = use_cuda_kernel  # accepted for compatibility: this build is always the CUDA path
         self.precision = precision or h.get("bvg_precision") or os.environ.get("BVG_PRECISION", "bf16")
-        if self.precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        # "bf16": bf16 operands on the tensor cores (>= 40 dB); "fp32": fp32 SIMT convolutions (<= 1e-5 of the reference);
+        # "bf16x3": fp32 storage, every convolution as three (option split_terms: 6, 9) bf16 tensor-core passes over three-term
+        # splits of both operands: 93-96 dB / 2e-5 on the full generator - the tensor cores' fp32 accumulation is the limit -
+        # at 8x (4.5x, 3x) the fp32 mode's speed
+        if self.precision not in ("bf16", "fp32", "bf16x3"):
+            raise ValueError("precision must be 'bf16', 'fp32' or 'bf16x3'")
         if h["resblock"] != "1":
             # AMPBlock2.forward has no return in the reference (bigvgan.py:232-236): not a usable configuration
             raise ValueError("Incorrect resblock class specified in hyperparameters. Got %s" % h["resblock"])
@@ -183,6 +187,8 @@ class BigVGAN(nn.Module):
                     _lib.check(lib.bvg_set_tensor(handle, name.encode(), t.data_ptr(), t.numel(), 1),
                                "bvg_set_tensor(%s)" % name)
             _lib.check(lib.bvg_finalize(handle), "bvg_finalize")
+            if self.precision == "bf16x3":
+                _lib.check(lib.bvg_set_option(handle, b"conv_impl", 3), "bvg_set_option")
             for k, v in self._options.items():
                 _lib.check(lib.bvg_set_option(handle, k.encode(), v), "bvg_set_option")
         except Exception:

@@ -55,6 +55,9 @@ static inline bool convtr_shape_ok(int k, int u) { return u >= 1 && k >= u && (k
 // per-utterance bias rows: out[b][r*Cp + c] = bias[c] + cb[c] + sum_e Wc[c][e] * emb[b][e]  (r < rep; pad entries zero)
 int cond_bias_launch(float* out, int64_t out_bs, const float* bias, const float* Wc, const float* cb, const float* emb, int B,
                      int E, int C, int Cp, int rep, cudaStream_t st);
+// x = b0 + b1 + b2 (three bf16 terms, exact to fp32's 24 bits): bf16 outputs for activations, fp32 containers for weights
+int split3_bf16(void* o0, void* o1, void* o2, const float* src, int64_t n, cudaStream_t st);
+int split3_f32(float* o0, float* o1, float* o2, const float* src, int64_t n, cudaStream_t st);
 // [B, T, C] fp32 -> [B, T, Cp] (cast to out_dtype, zero pad channels)
 int btc_pad_cast(void* dst, int out_dtype, const float* src, int64_t rows, int C, int Cp, cudaStream_t st);
 int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, const float* w, float bias, int B,

@@ -374,6 +374,46 @@ int btc_pad_cast(void* dst, int out_dtype, const float* src, int64_t rows, int C
   return BVG_OK;
 }
 
+// ---- fp32 values as sums of three bf16 terms (fp32-accurate convolutions on the bf16 tensor cores) -----------------------
+// x = b0 + b1 + b2 with b0 = bf16(x), b1 = bf16(x - b0), b2 = bf16(x - b0 - b1): the subtractions are exact in fp32 and
+// three 8-bit mantissas cover fp32's 24 bits (bf16 has fp32's exponent range, so nothing underflows that fp32 keeps).
+__global__ void split3_bf16_kernel(__nv_bfloat16* __restrict__ o0, __nv_bfloat16* __restrict__ o1, __nv_bfloat16* __restrict__ o2,
+                                   const float* __restrict__ src, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = BVG_LDG(src + i);
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b0);
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b1);
+    o0[i] = b0; o1[i] = b1; o2[i] = __float2bfloat16_rn(r2);
+  }
+}
+int split3_bf16(void* o0, void* o1, void* o2, const float* src, int64_t n, cudaStream_t st) {
+  if (n <= 0) return BVG_OK;
+  const int blocks = (int)(ceil_div(n, 256) < 148 * 32 ? ceil_div(n, 256) : 148 * 32);
+  split3_bf16_kernel<<<blocks, 256, 0, st>>>((__nv_bfloat16*)o0, (__nv_bfloat16*)o1, (__nv_bfloat16*)o2, src, n);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+// the same split kept in fp32 containers (weights: each term then goes through the ordinary bf16 packers)
+__global__ void split3_f32_kernel(float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
+                                  const float* __restrict__ src, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = src[i];
+    const float b0 = __bfloat162float(__float2bfloat16_rn(x));
+    const float r1 = x - b0;
+    const float b1 = __bfloat162float(__float2bfloat16_rn(r1));
+    o0[i] = b0; o1[i] = b1; o2[i] = __bfloat162float(__float2bfloat16_rn(r1 - b1));
+  }
+}
+int split3_f32(float* o0, float* o1, float* o2, const float* src, int64_t n, cudaStream_t st) {
+  if (n <= 0) return BVG_OK;
+  const int blocks = (int)(ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096);
+  split3_f32_kernel<<<blocks, 256, 0, st>>>(o0, o1, o2, src, n);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
 // ---- debug filler kernel (co-residency experiments) ------------------------------------------------------------
 __global__ void debug_spin_kernel(int iters, int mode, float* scratch, int64_t n) {
   float a = 1.0f + threadIdx.x * 1e-6f, b = 0.5f, c = 0.25f, d = 0.125f;

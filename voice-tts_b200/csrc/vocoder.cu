@@ -24,6 +24,7 @@
 namespace bvg {
 
 struct ConvW {
+  void* ws[3] = {nullptr, nullptr, nullptr};   // fp32 mode: the weight as three bf16 terms w = w0 + w1 + w2, each packed like `w`
   void* w = nullptr;       // packed Wp[k][Cout_r][Cin_p]
   float* bias = nullptr;   // [Cout_r]
   int Cin = 0, Cout = 0, Cin_p = 0, Cout_p = 0, Cout_n = 0, Cout_r = 0;
@@ -72,6 +73,7 @@ struct bvg_vocoder {
   bool finalized = false;
   // options
   int opt_graph = 0, opt_conv_impl = 0, opt_umma_variant = 0, opt_fast_sin = -1;
+  int opt_split_terms = 3;         // fp32 storage + tensor cores (conv_impl = 3): term pairs per convolution (3, 6 or 9)
   int opt_fuse_res = 1;            // conv2 of an AMP unit adds the residual AND applies the next unit's first activation (bf16 mode)
   int opt_fuse_act = 1;            // conv1 of an AMP unit applies the following activation in its epilogue (bf16 mode)
   int fuse_res_min_kc = 4096;      // smallest k * Cin whose conv2 takes the fused residual + activation epilogue
@@ -123,6 +125,9 @@ static void init_conv(ConvW& c, int Cin, int Cout, int k, int dil, int up, int g
 static int alloc_conv(ConvW& c, int w_dt) {
   int rc = dev_alloc(&c.w, (size_t)c.k * c.Cout_r * c.Cin_p * dtype_size(w_dt));
   if (rc) return rc;
+  if (w_dt == BVG_F32)
+    for (int i = 0; i < 3; ++i)
+      if ((rc = dev_alloc(&c.ws[i], (size_t)c.k * c.Cout_r * c.Cin_p * 2))) return rc;
   rc = dev_alloc((void**)&c.bias, (size_t)c.Cout_r * sizeof(float));
   if (rc) return rc;
   BVG_CUDA(cudaMemset(c.bias, 0, (size_t)c.Cout_r * sizeof(float)));
@@ -145,6 +150,8 @@ struct Buffers {
   float *cb_pre, *cb_up[8];            // per-utterance bias rows of conv_pre / ups[i] (conditioned generator only)
   void *mel, *p0, *nx, *a1[4], *m[4], *a2[4];
   float *x, *y[4], *y2[4], *xs;   // y / y2: the residual stream of a block ping-pongs (fused conv2 reads halo rows of its input)
+  void* sp[4][3];                 // fp32 mode: the conv input as three bf16 terms (per concurrently running block)
+  float* t[4];                    // fp32 mode: running sum of the term-pair convolutions
   int nb;
 };
 
@@ -180,13 +187,21 @@ static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
   const size_t o_x = take(nmax * 4);
   const size_t o_xs = take(nmax * 4);
   const int nb = n_block_streams(v);
-  size_t o_a1[4], o_m[4], o_a2[4], o_y[4], o_y2[4];
+  size_t o_a1[4], o_m[4], o_a2[4], o_y[4], o_y2[4], o_sp[4][3] = {}, o_t[4] = {};
+  const bool split = v->cfg.mode == BVG_MODE_FP32;
+  size_t nin = nmax;                                  // largest conv input: stage tensors, conv_pre's mel, ups[0]'s p0
+  if ((size_t)B * T0 * v->mel_p > nin) nin = (size_t)B * T0 * v->mel_p;
+  if ((size_t)B * T0 * v->Cp[0] > nin) nin = (size_t)B * T0 * v->Cp[0];
   for (int j = 0; j < nb; ++j) {
     o_a1[j] = take(nmax * es);
     o_m[j] = take(nmax * es);
     o_a2[j] = take(nmax * es);
     o_y[j] = take(nmax * 4);
     o_y2[j] = take(nmax * 4);
+    if (split) {
+      for (int q = 0; q < 3; ++q) o_sp[j][q] = take(nin * 2);
+      o_t[j] = take((nmax > (size_t)B * T0 * v->Cp[0] ? nmax : (size_t)B * T0 * v->Cp[0]) * 4);
+    }
   }
   if (out) {
     unsigned char* base = (unsigned char*)v->arena;
@@ -199,6 +214,8 @@ static size_t plan_buffers(const bvg_vocoder* v, int B, int T0, Buffers* out) {
       out->a1[j] = base + o_a1[j]; out->m[j] = base + o_m[j]; out->a2[j] = base + o_a2[j];
       out->y[j] = (float*)(base + o_y[j]);
       out->y2[j] = (float*)(base + o_y2[j]);
+      for (int q = 0; q < 3; ++q) out->sp[j][q] = split ? base + o_sp[j][q] : nullptr;
+      out->t[j] = split ? (float*)(base + o_t[j]) : nullptr;
     }
   }
   return off;
@@ -243,15 +260,67 @@ struct ProfScope {
 // anything enqueued outside a ProfScope (copies, event waits, graph launches) breaks the chain of shared events
 static inline void prof_break(bvg_vocoder* v) { v->prof_last = -1; }
 
+// fp32 storage on the tensor cores (bvg_set_option("conv_impl", 3) in BVG_MODE_FP32; Python precision "bf16x3"): activation
+// and weight are each the sum of three bf16 terms (exact to fp32's 24 bits) and the convolution is the sum of the term-pair
+// convolutions, (a0+a1+a2)(w0+w1+w2) ~ [a2w2 + a2w1 + a1w2 +] [a2w0 + a0w2 + a1w1 +] a1w0 + a0w1 + a0w0 - "split_terms" 9,
+// 6 or 3 (default) of them, smallest first - every pair one bf16 tcgen05 launch accumulating in fp32 (TMEM), chained through
+// the fp32 running sum `t`; bias / residual / scale / accumulate ride on the first and last pass.  bf16 x bf16 products are
+// exact in fp32, so with 6 or 9 terms the operands carry full fp32 precision - and the result still differs from the fp32
+// SIMT kernels by 1.8e-5 on the full generator (95.7 dB; SIMT 2.6e-6 / 112 dB): the tensor cores' fp32 accumulation is not
+// round-to-nearest, and a 768-channel k = 11 layer chains 528 accumulating MMAs per output.  That is why this is NOT the
+// <= 1e-5 parity mode, and why 3 terms (93.4 dB) are the default: measured on 16 x 10 s, 3 / 6 / 9 terms run at 1 150 / 674 /
+// 478 audio-s/s against 147 for the SIMT kernels and 4 000 for plain bf16 (41 dB).
+struct SplitPlan { ConvArgs first, mid, last; };
+static bool plan_conv_split(const ConvW& c, void* out, int out_dt, const float* res, const float* accum, float scale, int B,
+                            int64_t T, const float* bias, int64_t bias_bs, void* const sp[3], float* t, SplitPlan* pl) {
+  ConvArgs a;
+  a.in = sp[0]; a.w = c.ws[0]; a.bias = nullptr; a.out = t; a.res = res; a.accum = nullptr; a.scale = 1.f;
+  a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_F32;
+  a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
+  a.k = c.k; a.dil = c.dil;
+  pl->first = a;
+  pl->mid = a;
+  pl->mid.res = t;
+  pl->last = a;
+  pl->last.res = t; pl->last.accum = accum; pl->last.out = out; pl->last.out_dtype = out_dt; pl->last.bias = bias;
+  pl->last.bias_bs = bias_bs; pl->last.scale = scale;
+  return conv_umma_supported(pl->first) && conv_umma_supported(pl->mid) && conv_umma_supported(pl->last);
+}
+static int run_conv_split(bvg_vocoder* v, const ConvW& c, const float* in, SplitPlan& pl, int B, int64_t T, cudaStream_t st,
+                          void* const sp[3]) {
+  int rc = split3_bf16(sp[0], sp[1], sp[2], in, (int64_t)B * T * c.Cin_p, st);
+  if (rc) return rc;
+  // (activation term, weight term), smallest products first: split_terms = 9 runs all, 6 drops the pairs of weight <= 2^-24,
+  // 3 keeps a1w0 + a0w1 + a0w0 (weight >= 2^-8)
+  static const int order[9][2] = {{2, 2}, {2, 1}, {1, 2}, {2, 0}, {0, 2}, {1, 1}, {1, 0}, {0, 1}, {0, 0}};
+  const int q0 = v->opt_split_terms >= 9 ? 0 : (v->opt_split_terms >= 6 ? 3 : 6);   // 9, 6 or 3 term pairs
+  for (int q = q0; q < 9; ++q) {
+    ConvArgs& p = q == q0 ? pl.first : (q == 8 ? pl.last : pl.mid);
+    p.in = sp[order[q][0]];
+    p.w = c.ws[order[q][1]];
+    if ((rc = conv_umma_launch(p, v->opt_umma_variant, st))) return rc;
+  }
+  return BVG_OK;
+}
+
 static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, void* out, int out_dt,
                     const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st,
-                    const float* bias_rows = nullptr) {
+                    const float* bias_rows = nullptr, void* const* sp = nullptr, float* t = nullptr) {
   ConvArgs a;
   a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = res; a.accum = accum; a.scale = scale;
   if (bias_rows) { a.bias = bias_rows; a.bias_bs = c.Cout_r; }   // per-utterance rows: layer bias + cond(speaker_embedding)
   a.in_dtype = in_dt; a.w_dtype = v->act_dt; a.out_dtype = out_dt;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
   a.k = c.k; a.dil = c.dil;
+  if (v->cfg.mode == BVG_MODE_FP32 && v->opt_conv_impl == 3 && in_dt == BVG_F32 && sp && t && c.ws[0]) {
+    void* const spl[3] = {sp[0], sp[1], sp[2]};
+    SplitPlan pl;
+    if (plan_conv_split(c, out, out_dt, res, accum, scale, B, T, a.bias, a.bias_bs, spl, t, &pl)) {
+      ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
+      ps.cin = c.Cin; ps.cout = c.up > 0 ? -c.Cout : c.Cout; ps.k = c.k_torch; ps.dil = 300 + c.dil; ps.rows = (long long)B * T;
+      return run_conv_split(v, c, (const float*)in, pl, B, T, st, spl);
+    }
+  }
   bool umma = (v->cfg.mode == BVG_MODE_BF16) && v->opt_conv_impl != 1;
   if (umma && !conv_umma_supported(a)) {
     if (v->opt_conv_impl == 2) BVG_FAIL(BVG_EINVAL, "conv layer not supported by the tcgen05 kernel");
@@ -354,14 +423,17 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
   int rc = BVG_OK;
   if (nb > 1 && (rc = ensure_streams(v))) return rc;
   const bool cond = v->E > 0;
-  rc = run_conv(v, v->conv_pre, bf.mel, adt, bf.p0, adt, nullptr, nullptr, 1.f, B, T0, st, cond ? bf.cb_pre : nullptr);
+  void* const* sp_main = bf.sp[nb - 1];   // conv_pre / ups run on the caller's stream, like the last AMP block
+  float* t_main = bf.t[nb - 1];
+  rc = run_conv(v, v->conv_pre, bf.mel, adt, bf.p0, adt, nullptr, nullptr, 1.f, B, T0, st, cond ? bf.cb_pre : nullptr, sp_main,
+                t_main);
   if (rc) return rc;
   const void* stage_in = bf.p0;
   int64_t T = T0;
   for (int i = 0; i < v->nst; ++i) {
     // ConvTranspose1d: 3-tap conv over the input rows writing u*Cp phase channels == [B, u*T, Cp]
     rc = run_conv(v, v->ups[i], stage_in, adt, bf.x, BVG_F32, nullptr, nullptr, 1.f, B, T, st,
-                  (cond && !v->conds.empty()) ? bf.cb_up[i] : nullptr);
+                  (cond && !v->conds.empty()) ? bf.cb_up[i] : nullptr, sp_main, t_main);
     if (rc) return rc;
     T *= v->cfg.upsample_rates[i];
     const bool last_stage = (i == v->nst - 1);
@@ -387,7 +459,8 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
           rc = run_conv_act(v, v->convs1[ci], v->acts[ai + 1], bf.a1[slot], bf.a2[slot], B, T, sj);
           if (rc) return rc;
         } else {
-          rc = run_conv(v, v->convs1[ci], bf.a1[slot], adt, bf.m[slot], adt, nullptr, nullptr, 1.f, B, T, sj);
+          rc = run_conv(v, v->convs1[ci], bf.a1[slot], adt, bf.m[slot], adt, nullptr, nullptr, 1.f, B, T, sj, nullptr,
+                        bf.sp[slot], bf.t[slot]);
           if (rc) return rc;
           rc = run_act(v, v->acts[ai + 1], bf.m[slot], adt, bf.a2[slot], adt, B, T, sj);
           if (rc) return rc;
@@ -398,14 +471,15 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
             rc = run_conv_res_act(v, v->convs2[ci], v->acts[ai + 2], bf.a2[slot], bf.a1[slot], cur, ynext, B, T, sj);
             a1_ready = true;
           } else {
-            rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, ynext, BVG_F32, cur, nullptr, 1.f, B, T, sj);
+            rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, ynext, BVG_F32, cur, nullptr, 1.f, B, T, sj, nullptr, bf.sp[slot],
+                          bf.t[slot]);
           }
           cur = ynext;
         } else {
           const bool to_next = (j == v->nk - 1) && !last_stage;
           if (nb > 1 && j > 0) { prof_break(v); BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0)); }   // XS of block j-1
           rc = run_conv(v, v->convs2[ci], bf.a2[slot], adt, to_next ? bf.nx : (void*)bf.xs, to_next ? adt : BVG_F32, cur,
-                        j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, sj);
+                        j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, sj, nullptr, bf.sp[slot], bf.t[slot]);
           if (rc) return rc;
           if (nb > 1 && j < v->nk - 1) BVG_CUDA(cudaEventRecord(v->ev_blk[j % 3], sj));
         }
@@ -544,6 +618,20 @@ static int set_conv_tensor(bvg_vocoder* v, ConvW& c, bool is_weight, const float
     int rc = c.up > 0 ? pack_convtr_weight(c.w, v->act_dt, d_data, c.Cin, c.Cout, c.up, c.k_torch, c.Cout_p, c.Cout_r, c.Cin_p, 0)
                       : pack_conv_weight(c.w, v->act_dt, d_data, c.Cout, c.Cin, c.k, c.Cout_r, c.Cin_p, 0);
     if (rc) return rc;
+    if (c.ws[0]) {
+      // fp32 mode: w = w0 + w1 + w2 (bf16 terms), each packed for the tcgen05 kernels (run_conv_split)
+      float* tmp = nullptr;
+      BVG_CUDA(cudaMalloc((void**)&tmp, (size_t)3 * numel * sizeof(float)));
+      rc = split3_f32(tmp, tmp + numel, tmp + 2 * numel, d_data, numel, 0);
+      for (int q = 0; q < 3 && !rc; ++q)
+        rc = c.up > 0 ? pack_convtr_weight(c.ws[q], BVG_BF16, tmp + (size_t)q * numel, c.Cin, c.Cout, c.up, c.k_torch, c.Cout_p,
+                                           c.Cout_r, c.Cin_p, 0)
+                      : pack_conv_weight(c.ws[q], BVG_BF16, tmp + (size_t)q * numel, c.Cout, c.Cin, c.k, c.Cout_r, c.Cin_p, 0);
+      cudaError_t e = cudaDeviceSynchronize();
+      cudaFree(tmp);
+      if (rc) return rc;
+      BVG_CUDA(e);
+    }
     c.has_w = true;
   } else {
     if (numel != c.Cout) BVG_FAIL(BVG_EINVAL, "%s: expected %d elements, got %lld", name, c.Cout, (long long)numel);
@@ -637,10 +725,13 @@ int vocoder_set_tensor(bvg_vocoder* v, const char* name, const float* data, int6
     } else { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
   } else if (eat(s, "activation_post.")) {
     rc = set_act_tensor(v, v->act_post, s, d, numel, name);
-  } else if (v->E > 0 && (eat(s, "cond_layer.") || eat(s, "conds."))) {
-    CondW* cw = &v->cond_pre;
-    if (s[-2] == 's') {   // "conds.<i>."
-      if (!parse_int(s, &n) || n >= (int)v->conds.size() || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; cw = nullptr; }
+  } else if (v->E > 0 && (!strncmp(s, "cond_layer.", 11) || !strncmp(s, "conds.", 6))) {
+    CondW* cw = nullptr;
+    if (eat(s, "cond_layer.")) {
+      cw = &v->cond_pre;
+    } else {
+      eat(s, "conds.");
+      if (!parse_int(s, &n) || n >= (int)v->conds.size() || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
       else cw = &v->conds[n];
     }
     if (cw) {
@@ -855,7 +946,11 @@ extern "C" void bvg_destroy(bvg_vocoder* v) {
   if (!v) return;
   cudaSetDevice(v->cfg.device);
   cudaDeviceSynchronize();
-  auto free_conv = [](ConvW& c) { if (c.w) cudaFree(c.w); if (c.bias) cudaFree(c.bias); };
+  auto free_conv = [](ConvW& c) {
+    if (c.w) cudaFree(c.w);
+    if (c.bias) cudaFree(c.bias);
+    for (int q = 0; q < 3; ++q) if (c.ws[q]) cudaFree(c.ws[q]);
+  };
   auto free_act = [](ActW& a) { if (a.alpha) cudaFree(a.alpha); if (a.beta) cudaFree(a.beta); };
   free_conv(v->conv_pre);
   for (auto& c : v->ups) free_conv(c);
@@ -885,6 +980,7 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
   if (!strcmp(key, "graph")) v->opt_graph = value;
   else if (!strcmp(key, "conv_impl")) v->opt_conv_impl = value;
   else if (!strcmp(key, "umma_variant")) v->opt_umma_variant = value;
+  else if (!strcmp(key, "split_terms")) v->opt_split_terms = value;
   else if (!strcmp(key, "fast_sin")) v->opt_fast_sin = value;
   else if (!strcmp(key, "workspace_mb")) v->opt_ws_cap_mb = value;
   else if (!strcmp(key, "profile")) v->opt_profile = value;
