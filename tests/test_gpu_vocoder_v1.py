@@ -48,6 +48,12 @@ def test_v1_generator_vs_reference_golden(pkg, synth, cfg, golden, name):
     snr = O.snr_db(ref, wavb.cpu())
     print("%s bf16 SNR %.1f dB" % (name, snr))
     assert snr >= 33.0
+    mx = make(pkg, h, sd, "bf16x3")          # per-utterance bias rows ride on the last term-pair pass
+    with torch.no_grad():
+        wavx, _ = mx(latent.to(DEV), speaker_embedding=emb.to(DEV))
+    snrx = O.snr_db(ref, wavx.cpu())
+    print("%s bf16x3 SNR %.1f dB" % (name, snrx))
+    assert snrx >= 70.0
 
 
 def test_v1_speaker_encoder_module_and_batch_rows(pkg, synth, cfg):
