@@ -4,6 +4,8 @@
 //
 //   out[b,t,co] = scale*(bias[co] + sum_j sum_ci Wp[j][co][ci] * in[b, t+(j-(k-1)/2)*dil, ci] + res[b,t,co]) + accum[b,t,co]
 // zero outside [0,T)  (torch Conv1d with padding (k-1)*dil/2; bigvgan.py:59-66,76-83)
+#include <cstdlib>
+
 #include "conv.cuh"
 
 namespace bvg {
@@ -89,6 +91,126 @@ conv_simt_kernel(ConvArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Second-generation fp32 kernel for the wide layers (the hot kernel of the <= 1e-5 parity mode): 128 time rows x TC out
+// channels per block (TC = 128 or 64), 16-channel K slabs double-buffered in shared memory (the next slab's global loads are
+// in flight while the current one is multiplied), 8 x TC/16 register tile per thread fed by 128-bit shared loads.  Same
+// formula and the same fp32 FMA chain per output as conv_simt_kernel (taps outermost, channels ascending), so the two
+// kernels agree to the last bit and the choice between them is purely a matter of tile efficiency.
+constexpr int T2_T = 128, T2_K = 16, T2_PAD = 4;
+
+template <int TC>
+__global__ void __launch_bounds__(256, 2)
+conv_simt2_kernel(ConvArgs a) {
+  constexpr int NJ = TC / 16;          // out channels per thread: 8 or 4
+  constexpr int NG = NJ / 4;           // float4 groups per thread
+  constexpr int WLD = TC / 128 + 1;    // W slab: 16 floats of each of TC rows = TC*16/256 floats per thread / 4 = float4 loads (2 or 1)
+  __shared__ __align__(16) float Xs[2][T2_K][T2_T + T2_PAD];
+  __shared__ __align__(16) float Ws[2][T2_K][TC + T2_PAD];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int b = blockIdx.z;
+  const int64_t t0 = (int64_t)blockIdx.x * T2_T;
+  const int co0 = blockIdx.y * TC;
+  const float* in = reinterpret_cast<const float*>(a.in) + (int64_t)b * a.T * a.Cin_p;
+  const float* w = reinterpret_cast<const float*>(a.w);
+
+  float acc[8][NJ];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+
+  // loaders: X slab = 128 rows x 16 channels -> thread (row = tid % 128, 8 channels at (tid / 128) * 8): consecutive lanes own
+  // consecutive rows, so the transposed shared-memory stores are conflict-free.  W slab = TC rows x 16 channels likewise.
+  const int xrow = tid % 128, xc = (tid / 128) * 8;
+  const int wrow = tid % TC, wc = (tid / TC) * (TC == 128 ? 8 : 4);
+  const int center = (a.k - 1) / 2;
+  const int nslab = a.Cin_p / T2_K;
+  const int total = a.k * nslab;
+
+  float4 xr[2], wr[WLD];
+  auto gload = [&](int it) {
+    const int j = it / nslab, ci0 = (it % nslab) * T2_K;
+    const int64_t tsrc = t0 + xrow + (int64_t)(j - center) * a.dil;
+    if (tsrc >= 0 && tsrc < a.T) {
+      const float4* p = reinterpret_cast<const float4*>(in + tsrc * a.Cin_p + ci0 + xc);
+      xr[0] = BVG_LDG(p);
+      xr[1] = BVG_LDG(p + 1);
+    } else {
+      xr[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xr[1] = xr[0];
+    }
+    const float4* q = reinterpret_cast<const float4*>(w + ((int64_t)j * a.Cout_r + co0 + wrow) * a.Cin_p + ci0 + wc);
+#pragma unroll
+    for (int i = 0; i < WLD; ++i) wr[i] = __ldg(q + i);
+  };
+  auto sstore = [&](int buf) {
+    const float xv[8] = {xr[0].x, xr[0].y, xr[0].z, xr[0].w, xr[1].x, xr[1].y, xr[1].z, xr[1].w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) Xs[buf][xc + q][xrow] = xv[q];
+#pragma unroll
+    for (int i = 0; i < WLD; ++i) {
+      Ws[buf][wc + 4 * i + 0][wrow] = wr[i].x;
+      Ws[buf][wc + 4 * i + 1][wrow] = wr[i].y;
+      Ws[buf][wc + 4 * i + 2][wrow] = wr[i].z;
+      Ws[buf][wc + 4 * i + 3][wrow] = wr[i].w;
+    }
+  };
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int it = 0; it < total; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < total) gload(it + 1);
+#pragma unroll
+    for (int kk = 0; kk < T2_K; ++kk) {
+      const float4 xa = *reinterpret_cast<const float4*>(&Xs[buf][kk][ty * 4]);
+      const float4 xb = *reinterpret_cast<const float4*>(&Xs[buf][kk][64 + ty * 4]);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      float wv[NJ];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float4 wq = *reinterpret_cast<const float4*>(&Ws[buf][kk][g * 64 + tx * 4]);
+        wv[4 * g] = wq.x; wv[4 * g + 1] = wq.y; wv[4 * g + 2] = wq.z; wv[4 * g + 3] = wq.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+    }
+    if (it + 1 < total) {
+      sstore(buf ^ 1);       // the other buffer was last read one iteration ago, before the barrier below
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t t = t0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (t >= a.T) continue;
+    const int64_t rowoff = ((int64_t)b * a.T + t) * a.out_ld;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int co = co0 + (j / 4) * 64 + tx * 4 + (j % 4);
+      if (co >= a.Cout_n) continue;
+      float v = acc[i][j];
+      if (a.bias) v += BVG_LDG(a.bias + (int64_t)b * a.bias_bs + co);
+      if (a.res) v += BVG_LDG(a.res + rowoff + co);
+      v *= a.scale;
+      if (a.accum) v += BVG_LDG(a.accum + rowoff + co);
+      if (a.out_dtype == BVG_BF16) reinterpret_cast<__nv_bfloat16*>(a.out)[rowoff + co] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(a.out)[rowoff + co] = v;
+    }
+  }
+}
+
+static bool simt2_ok(const ConvArgs& a) {
+  return a.in_dtype == BVG_F32 && a.w_dtype == BVG_F32 && a.Cin_p % T2_K == 0 && a.Cout_n > 32 && a.Cout_r % 128 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0;
+}
+
 template <typename Tin, typename Tw>
 static int launch_simt(const ConvArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(a.T, TS_T), (unsigned)ceil_div(a.Cout_n, TS_C), (unsigned)a.B);
@@ -104,6 +226,18 @@ int conv_simt_launch(const ConvArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.T <= 0) return BVG_OK;
   if (a.Cin_p % 4 != 0) BVG_FAIL(BVG_EINVAL, "conv_simt: Cin_p=%d not a multiple of 4", a.Cin_p);
   typedef __nv_bfloat16 bf;
+  static const bool old_only = getenv("BVG_SIMT_V1") != nullptr;   // A/B timing
+  if (!old_only && simt2_ok(a)) {
+    if (a.Cout_n > 64) {
+      dim3 grid((unsigned)ceil_div(a.T, T2_T), (unsigned)ceil_div(a.Cout_n, 128), (unsigned)a.B);
+      conv_simt2_kernel<128><<<grid, 256, 0, st>>>(a);
+    } else {
+      dim3 grid((unsigned)ceil_div(a.T, T2_T), (unsigned)ceil_div(a.Cout_n, 64), (unsigned)a.B);
+      conv_simt2_kernel<64><<<grid, 256, 0, st>>>(a);
+    }
+    BVG_LAUNCHED();
+    return BVG_OK;
+  }
   if (a.in_dtype == BVG_F32 && a.w_dtype == BVG_F32) return launch_simt<float, float>(a, st);
   if (a.in_dtype == BVG_BF16 && a.w_dtype == BVG_BF16) return launch_simt<bf, bf>(a, st);
   if (a.in_dtype == BVG_BF16 && a.w_dtype == BVG_F32) return launch_simt<bf, float>(a, st);
