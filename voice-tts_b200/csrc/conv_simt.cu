@@ -97,10 +97,16 @@ conv_simt_kernel(ConvArgs a) {
 // in flight while the current one is multiplied), 8 x TC/16 register tile per thread fed by 128-bit shared loads.  Same
 // formula and the same fp32 FMA chain per output as conv_simt_kernel (taps outermost, channels ascending), so the two
 // kernels agree to the last bit and the choice between them is purely a matter of tile efficiency.
-constexpr int T2_T = 128, T2_K = 16, T2_PAD = 4;
+#ifndef BVG_SIMT2_K
+#define BVG_SIMT2_K 16
+#endif
+#ifndef BVG_SIMT2_MINBLK
+#define BVG_SIMT2_MINBLK 2
+#endif
+constexpr int T2_T = 128, T2_K = BVG_SIMT2_K, T2_PAD = 4;
 
 template <int TC>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, BVG_SIMT2_MINBLK)
 conv_simt2_kernel(ConvArgs a) {
   constexpr int NJ = TC / 16;          // out channels per thread: 8 or 4
   constexpr int NG = NJ / 4;           // float4 groups per thread
