@@ -261,3 +261,22 @@ def test_conv1d_fused_residual_activation_fp32_mode(ops):
     ya, y = ops.conv1d_res_act(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), al.to(DEV), be.to(DEV), tl, tl, d, "fp32", 0)
     assert (y.cpu().double() - yref).abs().max() <= 1e-5 * float(yref.abs().max())
     assert (ya.cpu().double() - aref).abs().max() <= 1e-5 * float(aref.abs().max())
+
+
+def test_fp32_simt_kernels_bit_identical():
+    """the second-generation fp32 SIMT kernel (128 x 128/64 tiles) runs the same FMA chain per output as the first (64 x 64):
+    tools/simt_ab.py prints an md5 of every result; BVG_SIMT_V1=1 selects the first kernel (read once per process)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({}, {"BVG_SIMT_V1": "1"}):
+        e = dict(os.environ)
+        e.pop("BVG_SIMT_V1", None)
+        e.update(env)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "simt_ab.py")], capture_output=True, text=True, env=e,
+                           cwd=root, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and outs[0].count("\n") == 4
