@@ -103,7 +103,9 @@ conv_simt_kernel(ConvArgs a) {
 #ifndef BVG_SIMT2_MINBLK
 #define BVG_SIMT2_MINBLK 2
 #endif
-constexpr int T2_T = 128, T2_K = BVG_SIMT2_K, T2_PAD = 4;
+constexpr int T2_T = 128, T2_K = BVG_SIMT2_K, T2_PAD = 4, T2_G = 20;
+template <int TC>
+constexpr int simt2_smem_bytes() { return (2 * T2_K * (T2_T + T2_PAD) + 2 * T2_K * (TC + T2_PAD) + (T2_T + TC) * T2_G) * 4; }
 
 template <int TC>
 __global__ void __launch_bounds__(256, BVG_SIMT2_MINBLK)
@@ -111,8 +113,15 @@ conv_simt2_kernel(ConvArgs a) {
   constexpr int NJ = TC / 16;          // out channels per thread: 8 or 4
   constexpr int NG = NJ / 4;           // float4 groups per thread
   constexpr int WLD = TC / 128 + 1;    // W slab: 16 floats of each of TC rows = TC*16/256 floats per thread / 4 = float4 loads (2 or 1)
-  __shared__ __align__(16) float Xs[2][T2_K][T2_T + T2_PAD];
-  __shared__ __align__(16) float Ws[2][T2_K][TC + T2_PAD];
+  // dynamic shared memory: transposed operand tiles Xs[2][16][132], Ws[2][16][TC+4] (double buffered) and the cp.async
+  // staging rows Xg[128][20], Wg[TC][20] in the global layout (20-float pitch: conflict-free 128-bit reads of a thread's own row)
+  extern __shared__ __align__(16) float smem_f[];
+  typedef float (*XsT)[T2_K][T2_T + T2_PAD];
+  typedef float (*WsT)[T2_K][TC + T2_PAD];
+  XsT Xs = reinterpret_cast<XsT>(smem_f);
+  WsT Ws = reinterpret_cast<WsT>(smem_f + 2 * T2_K * (T2_T + T2_PAD));
+  float* Xg = smem_f + 2 * T2_K * (T2_T + T2_PAD) + 2 * T2_K * (TC + T2_PAD);
+  float* Wg = Xg + T2_T * T2_G;
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int b = blockIdx.z;
@@ -121,11 +130,13 @@ conv_simt2_kernel(ConvArgs a) {
   const float* in = reinterpret_cast<const float*>(a.in) + (int64_t)b * a.T * a.Cin_p;
   const float* w = reinterpret_cast<const float*>(a.w);
 
-  float acc[8][NJ];
+  // accumulators as f32x2 pairs over adjacent out channels: fma.rn.f32x2 is two independent round-to-nearest FMAs (the
+  // result is bit-identical to scalar FMAs) but reads half as many register operands per FMA
+  unsigned long long acc[8][NJ / 2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NJ / 2; ++j) acc[i][j] = 0ull;
 
   // loaders: X slab = 128 rows x 16 channels -> thread (row = tid % 128, 8 channels at (tid / 128) * 8): consecutive lanes own
   // consecutive rows, so the transposed shared-memory stores are conflict-free.  W slab = TC rows x 16 channels likewise.
@@ -135,32 +146,40 @@ conv_simt2_kernel(ConvArgs a) {
   const int nslab = a.Cin_p / T2_K;
   const int total = a.k * nslab;
 
-  float4 xr[2], wr[WLD];
+  // Global -> shared with cp.async (no registers held across the FMA block, so the copies really are in flight while the
+  // current slab is multiplied; as register prefetch the compiler sank the loads below the block to save registers and the
+  // first shared-memory store behind it became the top stall).  Each thread stages and later transposes ITS OWN 32 (16)
+  // bytes, so only cp.async.wait_group orders the staging buffer.  Rows outside [0, T) are zero-filled (src-size 0).
+  const uint32_t xg_addr = (uint32_t)__cvta_generic_to_shared(Xg + xrow * T2_G + xc);
+  const uint32_t wg_addr = (uint32_t)__cvta_generic_to_shared(Wg + wrow * T2_G + wc);
   auto gload = [&](int it) {
     const int j = it / nslab, ci0 = (it % nslab) * T2_K;
     const int64_t tsrc = t0 + xrow + (int64_t)(j - center) * a.dil;
-    if (tsrc >= 0 && tsrc < a.T) {
-      const float4* p = reinterpret_cast<const float4*>(in + tsrc * a.Cin_p + ci0 + xc);
-      xr[0] = BVG_LDG(p);
-      xr[1] = BVG_LDG(p + 1);
-    } else {
-      xr[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      xr[1] = xr[0];
-    }
-    const float4* q = reinterpret_cast<const float4*>(w + ((int64_t)j * a.Cout_r + co0 + wrow) * a.Cin_p + ci0 + wc);
+    const bool ok = tsrc >= 0 && tsrc < a.T;
+    const float* p = in + (ok ? tsrc : 0) * a.Cin_p + ci0 + xc;
+    const int nb = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xg_addr), "l"(p), "r"(nb) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xg_addr + 16), "l"(p + 4), "r"(nb) : "memory");
+    const float* q = w + ((int64_t)j * a.Cout_r + co0 + wrow) * a.Cin_p + ci0 + wc;
 #pragma unroll
-    for (int i = 0; i < WLD; ++i) wr[i] = __ldg(q + i);
+    for (int i = 0; i < WLD; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wg_addr + 16 * i), "l"(q + 4 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto sstore = [&](int buf) {
-    const float xv[8] = {xr[0].x, xr[0].y, xr[0].z, xr[0].w, xr[1].x, xr[1].y, xr[1].z, xr[1].w};
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const float4 x0 = *reinterpret_cast<const float4*>(Xg + xrow * T2_G + xc);
+    const float4 x1 = *reinterpret_cast<const float4*>(Xg + xrow * T2_G + xc + 4);
+    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
     for (int q = 0; q < 8; ++q) Xs[buf][xc + q][xrow] = xv[q];
 #pragma unroll
     for (int i = 0; i < WLD; ++i) {
-      Ws[buf][wc + 4 * i + 0][wrow] = wr[i].x;
-      Ws[buf][wc + 4 * i + 1][wrow] = wr[i].y;
-      Ws[buf][wc + 4 * i + 2][wrow] = wr[i].z;
-      Ws[buf][wc + 4 * i + 3][wrow] = wr[i].w;
+      const float4 wq = *reinterpret_cast<const float4*>(Wg + wrow * T2_G + wc + 4 * i);
+      Ws[buf][wc + 4 * i + 0][wrow] = wq.x;
+      Ws[buf][wc + 4 * i + 1][wrow] = wq.y;
+      Ws[buf][wc + 4 * i + 2][wrow] = wq.z;
+      Ws[buf][wc + 4 * i + 3][wrow] = wq.w;
     }
   };
 
@@ -175,16 +194,21 @@ conv_simt2_kernel(ConvArgs a) {
       const float4 xa = *reinterpret_cast<const float4*>(&Xs[buf][kk][ty * 4]);
       const float4 xb = *reinterpret_cast<const float4*>(&Xs[buf][kk][64 + ty * 4]);
       const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-      float wv[NJ];
+      unsigned long long wv[NJ / 2];
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         const float4 wq = *reinterpret_cast<const float4*>(&Ws[buf][kk][g * 64 + tx * 4]);
-        wv[4 * g] = wq.x; wv[4 * g + 1] = wq.y; wv[4 * g + 2] = wq.z; wv[4 * g + 3] = wq.w;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wv[2 * g]) : "f"(wq.x), "f"(wq.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wv[2 * g + 1]) : "f"(wq.z), "f"(wq.w));
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        unsigned long long xx;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xv[i]));
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+        for (int j = 0; j < NJ / 2; ++j)
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i][j]) : "l"(xx), "l"(wv[j]));
+      }
     }
     if (it + 1 < total) {
       sstore(buf ^ 1);       // the other buffer was last read one iteration ago, before the barrier below
@@ -201,7 +225,9 @@ conv_simt2_kernel(ConvArgs a) {
     for (int j = 0; j < NJ; ++j) {
       const int co = co0 + (j / 4) * 64 + tx * 4 + (j % 4);
       if (co >= a.Cout_n) continue;
-      float v = acc[i][j];
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i][j / 2]));
+      float v = (j & 1) ? hi : lo;
       if (a.bias) v += BVG_LDG(a.bias + (int64_t)b * a.bias_bs + co);
       if (a.res) v += BVG_LDG(a.res + rowoff + co);
       v *= a.scale;
@@ -236,10 +262,12 @@ int conv_simt_launch(const ConvArgs& a, cudaStream_t st) {
   if (!old_only && simt2_ok(a)) {
     if (a.Cout_n > 64) {
       dim3 grid((unsigned)ceil_div(a.T, T2_T), (unsigned)ceil_div(a.Cout_n, 128), (unsigned)a.B);
-      conv_simt2_kernel<128><<<grid, 256, 0, st>>>(a);
+      BVG_CUDA(cudaFuncSetAttribute(conv_simt2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, simt2_smem_bytes<128>()));
+      conv_simt2_kernel<128><<<grid, 256, simt2_smem_bytes<128>(), st>>>(a);
     } else {
       dim3 grid((unsigned)ceil_div(a.T, T2_T), (unsigned)ceil_div(a.Cout_n, 64), (unsigned)a.B);
-      conv_simt2_kernel<64><<<grid, 256, 0, st>>>(a);
+      BVG_CUDA(cudaFuncSetAttribute(conv_simt2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, simt2_smem_bytes<64>()));
+      conv_simt2_kernel<64><<<grid, 256, simt2_smem_bytes<64>(), st>>>(a);
     }
     BVG_LAUNCHED();
     return BVG_OK;
