@@ -269,7 +269,7 @@ static inline void prof_break(bvg_vocoder* v) { v->prof_last = -1; }
 // SIMT kernels by 1.8e-5 on the full generator (95.7 dB; SIMT 2.6e-6 / 112 dB): the tensor cores' fp32 accumulation is not
 // round-to-nearest, and a 768-channel k = 11 layer chains 528 accumulating MMAs per output.  That is why this is NOT the
 // <= 1e-5 parity mode, and why 3 terms (93.4 dB) are the default: measured on 16 x 10 s, 3 / 6 / 9 terms run at 1 150 / 674 /
-// 478 audio-s/s against 147 for the SIMT kernels and 4 000 for plain bf16 (41 dB).
+// 478 audio-s/s against 147-223 for the SIMT kernels (first / second generation) and 4 000 for plain bf16 (41 dB).
 struct SplitPlan { ConvArgs first, mid, last; };
 static bool plan_conv_split(const ConvW& c, void* out, int out_dt, const float* res, const float* accum, float scale, int B,
                             int64_t T, const float* bias, int64_t bias_bs, void* const sp[3], float* t, SplitPlan* pl) {
