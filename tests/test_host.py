@@ -29,6 +29,29 @@ def test_library_exports_every_declared_symbol():
     assert lib.bvg_abi_version() == 2
 
 
+def test_config_struct_matches_header(tmp_path):
+    """the ctypes mirror of `bvg_config` (voice-tts_b200/_lib.py) has the size and field offsets a C compiler gives the
+    struct in include/bvg_b200.h (a drifted mirror would hand the library a garbled configuration)"""
+    import importlib
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib = importlib.import_module("voice-tts_b200._lib")
+    names = [n for n, _ in _lib.BvgConfig._fields_]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bvg_b200.h"\nint main(void){printf("%zu", sizeof(bvg_config));'
+                   + "".join('printf(" %%zu", offsetof(bvg_config, %s));' % n for n in names) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert vals[0] == ctypes.sizeof(_lib.BvgConfig)
+    assert vals[1:] == [getattr(_lib.BvgConfig, n).offset for n in names]
+    hdr = open(os.path.join(ROOT, "include", "bvg_b200.h")).read()
+    body = hdr[hdr.index("typedef struct bvg_config {"):hdr.index("} bvg_config;")]
+    assert len(re.findall(r"^\s*int\s+\w+", body, re.M)) == len(names)      # every header field is mirrored
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
 def test_compute_entry_points_fail_loudly_without_gpu():
     import importlib
