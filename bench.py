@@ -471,6 +471,34 @@ def main():
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": "oracle port of the reference torch path, fp32, 1 utterance x 172 frames (2.0 s), "
                                          "median of 3 after 1 warm-up, %.2f s per forward, %s" % (med, cpu_model_name())}
+    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_cpu_baseline:
+        # the other precision modes on the same workload (reported beside the headline, not part of it): "fp32" is the
+        # <= 1e-5 parity mode (SIMT convolutions), "bf16x3" fp32 storage with three bf16 tensor-core passes per convolution
+        out["precision_modes"] = {}
+        del model
+        torch.cuda.empty_cache()
+        for prec in ("bf16x3", "fp32"):
+            try:
+                m2 = pkg.BigVGAN(h, precision=prec)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    m2.remove_weight_norm()
+                m2.load_state_dict(sd)
+                m2 = m2.to(dev).eval()
+                with torch.no_grad():
+                    m2(mel)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(2):
+                        m2(mel)
+                    e1.record()
+                    torch.cuda.synchronize()
+                msp = e0.elapsed_time(e1) / 2
+                out["precision_modes"][prec] = {"value": audio_s_step / (msp * 1e-3), "unit": UNIT, "ms_per_step": msp}
+                del m2
+                torch.cuda.empty_cache()
+            except Exception as e:  # a reported extra must never cost the headline line
+                out["precision_modes"][prec] = {"error": str(e)[:200]}
     if rank == 0 and args.act_sweep:
         out["activation_sweep"] = act_sweep(dev, pk)
     if rank == 0:
