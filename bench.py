@@ -255,7 +255,7 @@ def top_launch_stats(model, pk):
         with open(path) as f:
             for ln in f.read().splitlines()[1:]:
                 cat, cin, cout, k, dil, rows, ms, work, rate = ln.split(",")
-                if cat != "0":
+                if cat not in ("0", "4"):
                     continue
                 mode = int(dil) // 100
                 key = (int(cin), int(cout), int(k), mode)
@@ -268,7 +268,8 @@ def top_launch_stats(model, pk):
             return None
         key, (n, ms, work) = max(groups.items(), key=lambda kv: kv[1][1])
         tf = work / (ms * 1e-3) / 1e12
-        kind = {0: "plain epilogue", 1: "following Activation1d in the epilogue", 2: "residual + following Activation1d in the epilogue"}[key[3]]
+        kind = {0: "plain epilogue", 1: "following Activation1d in the epilogue", 2: "residual + following Activation1d in the epilogue",
+                3: "bf16x3 split", 4: "whole AMP unit: act + conv + act + conv + residual in one kernel, flops of both convs"}.get(key[3], "?")
         return {"layer": "Conv1d %d->%d k=%d (%s)" % (key[0], abs(key[1]), key[2], kind), "launches": n,
                 "avg_launch_ms": round(ms / n, 4), "achieved": round(tf, 1), "unit": "TFLOP/s",
                 "frac_of_sustained_peak": round(tf / pk["bf16_tflops_sustained"], 4),
@@ -405,7 +406,11 @@ def main():
     s_ms, s_flops, s_n = prof["conv_simt"]
     a_ms, a_bytes, a_n = prof["activation"]
     o_ms, _, o_n = prof["other"]
-    tot = c_ms + s_ms + a_ms + o_ms
+    u_ms, u_flops, u_n = prof.get("amp_unit", (0.0, 0.0, 0))
+    tot = c_ms + s_ms + a_ms + o_ms + u_ms
+    # the whole-AMP-unit kernels (amp_unit.cu) are tcgen05 conv kernels with both activations inside: they count as conv
+    # launches with the flops of their two convolutions
+    c_ms, c_flops, c_n = c_ms + u_ms, c_flops + u_flops, c_n + u_n
     conv_ms, conv_flops, conv_n, conv_name = (c_ms, c_flops, c_n, "conv_umma2_kernel + conv_umma2a_kernel (tcgen05 implicit-GEMM Conv1d/ConvTranspose1d; the a-variant carries the following Activation1d in its epilogue)") \
         if c_n else (s_ms, s_flops, s_n, "conv_simt_kernel (fp32)")
     tensor_peak = pk["bf16_tflops_sustained"]
@@ -454,7 +459,8 @@ def main():
         "roofline": roofline,
         "roofline_activation": roofline_act,
         "time_split_ms_per_step": {"conv_tcgen05": c_ms / args.steps, "conv_simt": s_ms / args.steps,
-                                   "activation": a_ms / args.steps, "other": o_ms / args.steps},
+                                   "activation": a_ms / args.steps, "other": o_ms / args.steps,
+                                   "of_which_amp_unit_kernels": u_ms / args.steps},
         "x_realtime_per_gpu": value / world,
         "profile_pass_ms_per_step": ms_prof / args.steps,
         "serial_schedule": {"value": world * audio_s_step * args.steps / (ms_serial * 1e-3), "unit": UNIT,

@@ -19,6 +19,7 @@
  *                           torch/act.py:25-30 (replicate-pad edges exactly as the torch path)
  *   bvg_conv1d_fwd       <- torch.nn.Conv1d as built at bigvgan.py:59-66,76-83,285-287,348-350
  *   bvg_convtr1d_fwd     <- torch.nn.ConvTranspose1d as built at bigvgan.py:306-312
+ *   bvg_amp_unit_fwd     <- one iteration of AMPBlock1.forward, bigvgan.py:132-141 (+ the mean of :369-375)
  *   bvg_create/..._fwd   <- BigVGAN.__init__/forward/remove_weight_norm  bigvgan.py:266-400,
  *                           called from indextts/infer_v2.py:155-158,735
  *   bvg_vocoder_fwd_cond <- the speaker-conditioned IndexTTS-v1 generator, indextts/BigVGAN/models.py:130-250
@@ -130,6 +131,22 @@ int bvg_conv1d_res_act_fwd(float* dst_act, float* dst_y, const float* src, const
                            const float* down_taps, int B, int Cin, int Cout, int64_t T, int k, int dilation, int mode,
                            bvg_stream_t stream);
 
+/* One whole AMPBlock1 unit - one iteration of the loop in AMPBlock1.forward (bigvgan.py:132-141):
+ *   xt = a1(x); xt = c1(xt); xt = a2(xt); xt = c2(xt); x = xt + x
+ * with the resblock mean of bigvgan.py:369-375 foldable into the result:
+ *   dst = (x + conv1d_k(act2(conv1d_{k,dil}(act1(x)) )) ) * scale + accum        x, dst, accum: fp32 [B, C, T]
+ * w1 / w2: [C, C, k] (torch layout), b1 / b2: [C] or NULL, alpha*_log / beta*_log: [C] fp32 log-scale device arrays,
+ * up_taps / down_taps: 12 host floats (both activations share them, as every Activation1d of the reference does).
+ * BVG_MODE_BF16 runs ONE kernel for C <= 96 (the activations run in registers beside the tcgen05 convolutions, the
+ * intermediates never leave the SM); otherwise, or with flags bit 0 set, the four layers run one after the other.
+ * flags bit 1: fail with BVG_EINVAL instead of falling back to the layer-by-layer form. */
+#define BVG_UNIT_LAYERWISE 1
+#define BVG_UNIT_REQUIRE_FUSED 2
+int bvg_amp_unit_fwd(float* dst, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* alpha1_log, const float* beta1_log, const float* alpha2_log, const float* beta2_log,
+                     const float* up_taps, const float* down_taps, const float* accum, float scale, int out_bf16,
+                     int B, int C, int64_t T, int k, int dilation, int mode, int flags, bvg_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Whole generator.  Build: bvg_create -> bvg_set_tensor for every state-dict
  * tensor (folded weights, reference key names) -> bvg_finalize -> forward calls.
@@ -186,16 +203,18 @@ int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
  * "fast_sin" (0/1), "workspace_mb" (micro-batching cap), "profile" (0/1: one CUDA-event pair per launch, read back with
  * bvg_profile_read), "fuse_act" (0 off, 1 measured policy, 2 always: conv1 + following activation in one kernel),
  * "fuse_res" / "fuse_res_min_kc" (conv2 + residual + next activation in one kernel: 0 off, 1 when k*Cin >= min_kc,
- * 2 always), "streams" (3 [default]: the AMP blocks of a stage on separate internal streams that fork from and join the caller's
+ * 2 always), "fuse_unit" (1 [default]: whole AMP units of <= 96-channel stages as ONE kernel, bvg_amp_unit_fwd; 0: layer by
+ * layer), "streams" (3 [default]: the AMP blocks of a stage on separate internal streams that fork from and join the caller's
  * stream; 1: serial; the result is bit-identical either way), "umma_variant" (debug).  Options that change the workspace layout drop captured graphs. */
 int bvg_set_option(bvg_vocoder* v, const char* key, int value);
 /* Debug only: filler kernel for co-residency experiments (mode 0: FMA spin, mode 1: streams `scratch`). */
 int bvg_debug_spin(int blocks, int threads, int iters, int mode, float* scratch, int64_t scratch_elems, bvg_stream_t stream);
 
 /* per-kernel CUDA-event timing (set option "profile"=1 first; disables graph replay while on):
- * category 0 = tcgen05 conv, 1 = SIMT conv, 2 = fused activation, 3 = other.  Returns the summed
+ * category 0 = tcgen05 conv, 1 = SIMT conv, 2 = fused activation, 3 = other, 4 = whole AMP unit in one kernel
+ * (work = the flops of its two convolutions).  Returns the summed
  * duration [ms], the summed algorithmic work (flops for convs, bytes for activations) and the
- * number of launches since the last read; reading category 3 clears the records. */
+ * number of launches since the last read; reading category 3 clears the records (read it last). */
 int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double* work, int* launches);
 /* writes one CSV line per recorded launch (category, shape, ms, work, rate) to `path`; does not clear */
 int bvg_profile_dump(bvg_vocoder* v, const char* path);

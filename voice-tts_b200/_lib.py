@@ -10,6 +10,7 @@ F32, BF16 = 0, 1
 MODE_FP32, MODE_BF16 = 0, 1
 SNAKE, SNAKEBETA = 0, 1
 ACT_FAST_SIN = 1
+UNIT_LAYERWISE, UNIT_REQUIRE_FUSED = 1, 2
 
 _ERR = {0: "BVG_OK", -1: "BVG_EINVAL", -2: "BVG_EDTYPE", -3: "BVG_EALIGN", -4: "BVG_ECUDA",
         -5: "BVG_ENODEV", -6: "BVG_ENOMEM", -7: "BVG_ESTATE"}
@@ -43,6 +44,7 @@ SYMBOLS = {
     "bvg_conv1d_res_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_conv1d_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_conv1d_res_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
+    "bvg_amp_unit_fwd": (_i, [_vp] * 10 + [_fp, _fp, _vp, _f, _i, _i, _i, _i64, _i, _i, _i, _i, _vp]),
     "bvg_convtr1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "bvg_create": (_i, [ctypes.POINTER(BvgConfig), ctypes.POINTER(_vp)]),
     "bvg_destroy": (None, [_vp]),

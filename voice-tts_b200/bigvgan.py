@@ -265,7 +265,8 @@ class BigVGAN(nn.Module):
         out = {}
         if self._hid is None:
             return out
-        for cat, name in enumerate(("conv_tcgen05", "conv_simt", "activation", "other")):
+        # category 3 ("other") clears the records: read it last
+        for cat, name in ((0, "conv_tcgen05"), (1, "conv_simt"), (2, "activation"), (4, "amp_unit"), (3, "other")):
             ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
             _lib.check(_lib.load().bvg_profile_read(ops._HANDLES[self._hid][0], cat, ctypes.byref(ms),
                                                     ctypes.byref(work), ctypes.byref(n)), "bvg_profile_read")

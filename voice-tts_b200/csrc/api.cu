@@ -264,6 +264,87 @@ int bvg_convtr1d_fwd(float* dst, const float* src, const float* weight, const fl
   return dense_layer(dst, src, weight, bias, B, Cin, Cout, T, k, 1, stride, mode, (cudaStream_t)stream);
 }
 
+// One AMPBlock1 unit on the reference layout (tests, single-unit callers): transposes + packing around amp_unit.cu
+// (BVG_MODE_BF16, one kernel) or around the layer-by-layer composition act -> conv -> act -> conv + residual.
+int bvg_amp_unit_fwd(float* dst, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* alpha1_log, const float* beta1_log, const float* alpha2_log, const float* beta2_log,
+                     const float* up_taps, const float* down_taps, const float* accum, float scale, int out_bf16, int B,
+                     int C, int64_t T, int k, int dilation, int mode, int flags, bvg_stream_t stream) {
+  if (mode != BVG_MODE_FP32 && mode != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_amp_unit_fwd: unknown mode %d", mode);
+  if (B < 0 || C <= 0 || T < 0 || k <= 0 || k % 2 != 1 || dilation < 1) BVG_FAIL(BVG_EINVAL, "bvg_amp_unit_fwd: bad dimension");
+  if (out_bf16 && mode != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "bvg_amp_unit_fwd: bf16 rounding of the result needs BVG_MODE_BF16");
+  if (B == 0 || T == 0) return BVG_OK;
+  if (!dst || !x || !w1 || !w2 || !alpha1_log || !beta1_log || !alpha2_log || !beta2_log || !up_taps || !down_taps)
+    BVG_FAIL(BVG_EINVAL, "bvg_amp_unit_fwd: null pointer");
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dt = mode == BVG_MODE_BF16 ? BVG_BF16 : BVG_F32;
+  const size_t es = dtype_size(dt);
+  const int Cp = pad_channels(C, 16), Cr = round_up(Cp, 128);
+  Taps taps;
+  host_taps(&taps, up_taps, down_taps);
+  const size_t a = 1024;
+  auto up_a = [&](size_t v) { return (v + a - 1) / a * a; };
+  const size_t b_f = up_a((size_t)B * T * Cp * 4), b_o = up_a((size_t)B * T * Cp * es), b_w = up_a((size_t)k * Cr * Cp * es),
+               b_v = up_a((size_t)Cr * 4);
+  unsigned char* blk = nullptr;
+  BVG_CUDA(cudaMallocAsync((void**)&blk, 3 * b_f + 3 * b_o + 2 * b_w + 6 * b_v, st));
+  unsigned char* q = blk;
+  float* xin = (float*)q; q += b_f;
+  float* yout = (float*)q; q += b_f;
+  float* acc = (float*)q; q += b_f;
+  void* t1 = q; q += b_o;
+  void* t2 = q; q += b_o;
+  void* t3 = q; q += b_o;
+  void* wp1 = q; q += b_w;
+  void* wp2 = q; q += b_w;
+  float* vec = (float*)q;   // bias1, bias2, alpha1, beta1, alpha2, beta2 (zero padded)
+  float* pv[6];
+  for (int i = 0; i < 6; ++i) pv[i] = (float*)((unsigned char*)vec + i * b_v);
+  const float* srcv[6] = {b1, b2, alpha1_log, beta1_log, alpha2_log, beta2_log};
+  do {
+    cudaError_t e = cudaMemsetAsync(vec, 0, 6 * b_v, st);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+      if (srcv[i]) e = cudaMemcpyAsync(pv[i], srcv[i], C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_error("bvg_amp_unit_fwd: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; break; }
+    if ((rc = bct_to_btc(xin, BVG_F32, x, B, C, Cp, T, st))) break;
+    if (accum && (rc = bct_to_btc(acc, BVG_F32, accum, B, C, Cp, T, st))) break;
+    if ((rc = pack_conv_weight(wp1, dt, w1, C, C, k, Cr, Cp, st))) break;
+    if ((rc = pack_conv_weight(wp2, dt, w2, C, C, k, Cr, Cp, st))) break;
+    AmpUnitArgs ua;
+    ua.x = xin; ua.out = yout; ua.accum = accum ? acc : nullptr; ua.scale = scale; ua.out_bf16 = out_bf16;
+    ua.w1 = wp1; ua.w2 = wp2; ua.bias1 = pv[0]; ua.bias2 = pv[1];
+    ua.al1 = pv[2]; ua.be1 = pv[3]; ua.al2 = pv[4]; ua.be2 = pv[5];
+    ua.taps1 = taps; ua.taps2 = taps;
+    ua.B = B; ua.T = T; ua.C = C; ua.Cp = Cp; ua.ld = Cp; ua.k = k; ua.dil = dilation;
+    const bool fused = dt == BVG_BF16 && !(flags & 1) && amp_unit_supported(ua);
+    if ((flags & 2) && !fused) { set_error("bvg_amp_unit_fwd: the one-kernel form does not take this unit"); rc = BVG_EINVAL; break; }
+    if (fused) {
+      if ((rc = amp_unit_launch(ua, st))) break;
+    } else {
+      // a1 -> c1 -> a2 -> c2 + residual, layer by layer
+      const bool fast = dt == BVG_BF16;
+      if ((rc = act1d_cl_launch(t1, xin, pv[2], pv[3], taps, B, T, Cp, BVG_F32, dt, fast, st))) break;
+      ConvArgs ca;
+      ca.in = t1; ca.w = wp1; ca.bias = pv[0]; ca.out = t2; ca.res = nullptr; ca.accum = nullptr; ca.scale = 1.f;
+      ca.in_dtype = dt; ca.w_dtype = dt; ca.out_dtype = dt;
+      ca.B = B; ca.T = T; ca.Cin_p = Cp; ca.Cout_n = Cp; ca.Cout_r = Cr; ca.out_ld = Cp; ca.k = k; ca.dil = dilation;
+      rc = (dt == BVG_BF16 && conv_umma_supported(ca)) ? conv_umma_launch(ca, 0, st) : conv_simt_launch(ca, st);
+      if (rc) break;
+      if ((rc = act1d_cl_launch(t3, t2, pv[4], pv[5], taps, B, T, Cp, dt, dt, fast, st))) break;
+      ca.in = t3; ca.w = wp2; ca.bias = pv[1]; ca.out = yout; ca.res = xin; ca.accum = accum ? acc : nullptr; ca.scale = scale;
+      ca.out_dtype = out_bf16 ? BVG_BF16 : BVG_F32; ca.dil = 1;
+      if (ca.accum && !ca.res) { rc = BVG_EINVAL; break; }
+      rc = (dt == BVG_BF16 && conv_umma_supported(ca)) ? conv_umma_launch(ca, 0, st) : conv_simt_launch(ca, st);
+      if (rc) break;
+    }
+    rc = btc_to_bct(dst, yout, out_bf16 ? BVG_BF16 : BVG_F32, B, C, Cp, T, st);
+  } while (0);
+  cudaFreeAsync(blk, st);
+  return rc;
+}
+
 // Debug: a filler kernel for co-residency experiments (tools/coresident_probe.py): `blocks` x `threads` threads spin for
 // `iters` iterations; mode 0 = FMA only (no memory traffic), mode 1 = stream a scratch buffer through ld.global.cg / st.
 int bvg_debug_spin(int blocks, int threads, int iters, int mode, float* scratch, int64_t scratch_elems, bvg_stream_t stream) {

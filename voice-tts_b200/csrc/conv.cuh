@@ -40,6 +40,28 @@ int conv_act_fused_launch(const ConvArgs& a, const float* alpha_log, const float
 // C channels per row are processed; ld (0 = C) is the row pitch in elements
 int act1d_cl_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,
                     int B, int64_t T, int C, int in_dtype, int out_dtype, bool fast, cudaStream_t st, int ld = 0);
+// One AMPBlock1 unit y = x + c2(a2(c1(a1(x)))) (bigvgan.py:132-141) as one kernel for <= 96-channel stages (amp_unit.cu).
+// x / out / accum: channels-last fp32 [B, T, ld] (out bf16 when out_bf16); weights packed bf16 Wp[k][128][Cp] as the
+// tcgen05 conv kernels take them (replicated rows for <= 64 channels), bias [128] fp32, alpha / beta [Cp] log scale.
+//   out = (conv2(...) + bias2 + x) * scale [+ accum]
+struct AmpUnitArgs {
+  const float* x = nullptr;
+  void* out = nullptr;
+  const float* accum = nullptr;
+  float scale = 1.f;
+  int out_bf16 = 0;
+  const void *w1 = nullptr, *w2 = nullptr;
+  const float *bias1 = nullptr, *bias2 = nullptr;
+  const float *al1 = nullptr, *be1 = nullptr, *al2 = nullptr, *be2 = nullptr;
+  Taps taps1, taps2;
+  int B = 0;
+  int64_t T = 0;
+  int C = 0, Cp = 0, ld = 0;
+  int k = 0, dil = 1;
+};
+bool amp_unit_supported(const AmpUnitArgs& a);
+int amp_unit_launch(const AmpUnitArgs& a, cudaStream_t st);
+
 int act1d_bct_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log, const Taps& taps,
                      int B, int C, int64_t T, int dtype, bool fast, cudaStream_t st);
 

@@ -77,6 +77,7 @@ struct bvg_vocoder {
   int opt_fuse_res = 1;            // conv2 of an AMP unit adds the residual AND applies the next unit's first activation (bf16 mode)
   int opt_fuse_act = 1;            // conv1 of an AMP unit applies the following activation in its epilogue (bf16 mode)
   int fuse_res_min_kc = 4096;      // smallest k * Cin whose conv2 takes the fused residual + activation epilogue
+  int opt_fuse_unit = 1;           // whole AMP units of <= 96-channel stages as one kernel (amp_unit.cu; bf16 mode)
   int opt_streams = 3;             // AMP blocks of one stage run on up to this many streams (1 = serial); see DESIGN.md 8.5
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // internal streams for AMP blocks 0 .. nk-2
   cudaEvent_t ev_fork = nullptr, ev_blk[3] = {nullptr, nullptr, nullptr};
@@ -228,7 +229,7 @@ static int max_microbatch(const bvg_vocoder* v, int B, int T0) {
   return b;
 }
 
-enum { CAT_CONV_UMMA = 0, CAT_CONV_SIMT = 1, CAT_ACT = 2, CAT_OTHER = 3, CAT_N = 4 };
+enum { CAT_CONV_UMMA = 0, CAT_CONV_SIMT = 1, CAT_ACT = 2, CAT_OTHER = 3, CAT_UNIT = 4, CAT_N = 5 };
 
 static cudaEvent_t prof_event(bvg_vocoder* v) {
   cudaEvent_t e = nullptr;
@@ -400,6 +401,35 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
 }
 
+// One whole AMP unit (a1 -> c1 -> a2 -> c2 + residual, bigvgan.py:132-141) as ONE launch for the narrow stages
+static void unit_args(const bvg_vocoder* v, int stage, const ConvW& c1, const ConvW& c2, const ActW& a1, const ActW& a2,
+                      const float* x, void* out, int out_bf16, const float* accum, float scale, int B, int64_t T,
+                      AmpUnitArgs* u) {
+  u->x = x; u->out = out; u->accum = accum; u->scale = scale; u->out_bf16 = out_bf16;
+  u->w1 = c1.w; u->w2 = c2.w; u->bias1 = c1.bias; u->bias2 = c2.bias;
+  u->al1 = a1.alpha; u->be1 = a1.beta; u->al2 = a2.alpha; u->be2 = a2.beta;
+  u->taps1 = a1.taps; u->taps2 = a2.taps;
+  u->B = B; u->T = T; u->C = v->C[stage + 1]; u->Cp = v->Cp[stage + 1]; u->ld = v->Cp[stage + 1];
+  u->k = c1.k; u->dil = c1.dil;
+}
+static bool can_fuse_unit(const bvg_vocoder* v, int stage, const ConvW& c1, const ConvW& c2, const ActW& a1, const ActW& a2,
+                          const float* x, void* out, int B, int64_t T) {
+  if (!v->opt_fuse_unit || v->cfg.mode != BVG_MODE_BF16 || v->opt_conv_impl == 1 || v->opt_fast_sin == 0) return false;
+  if (c1.Cout_r != 128 || c2.Cout_r != 128 || c1.k != c2.k || c2.dil != 1 || c1.Cin_p != c1.Cout_n) return false;
+  AmpUnitArgs u;
+  unit_args(v, stage, c1, c2, a1, a2, x, out, 0, nullptr, 1.f, B, T, &u);
+  return amp_unit_supported(u);
+}
+static int run_unit(bvg_vocoder* v, int stage, const ConvW& c1, const ConvW& c2, const ActW& a1, const ActW& a2, const float* x,
+                    void* out, int out_bf16, const float* accum, float scale, int B, int64_t T, cudaStream_t st) {
+  AmpUnitArgs u;
+  unit_args(v, stage, c1, c2, a1, a2, x, out, out_bf16, accum, scale, B, T, &u);
+  // work: the algorithmic flops of both convolutions (the two activations cost no algorithmic HBM bytes here)
+  ProfScope ps(v, st, CAT_UNIT, 2.0 * 2.0 * c1.Cout * c1.Cin * c1.k_torch * (double)T * B);
+  ps.cin = c1.Cin; ps.cout = c1.Cout; ps.k = c1.k_torch; ps.dil = 400 + c1.dil; ps.rows = (long long)B * T;
+  return amp_unit_launch(u, st);
+}
+
 // internal streams / events for the concurrent AMP blocks (created on first use)
 static int ensure_streams(bvg_vocoder* v) {
   for (int i = 0; i < 3; ++i) {
@@ -449,6 +479,22 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
       for (int l = 0; l < v->nd; ++l) {
         const int ci = (i * v->nk + j) * v->nd + l;
         const int ai = (i * v->nk + j) * 2 * v->nd + 2 * l;
+        if (!a1_ready && can_fuse_unit(v, i, v->convs1[ci], v->convs2[ci], v->acts[ai], v->acts[ai + 1], cur, bf.y[slot], B, T)) {
+          if (l < v->nd - 1) {
+            float* ynext = (l & 1) ? bf.y2[slot] : bf.y[slot];
+            rc = run_unit(v, i, v->convs1[ci], v->convs2[ci], v->acts[ai], v->acts[ai + 1], cur, ynext, 0, nullptr, 1.f, B, T, sj);
+            cur = ynext;
+          } else {
+            const bool to_next = (j == v->nk - 1) && !last_stage;
+            if (nb > 1 && j > 0) { prof_break(v); BVG_CUDA(cudaStreamWaitEvent(sj, v->ev_blk[(j - 1) % 3], 0)); }   // XS of block j-1
+            rc = run_unit(v, i, v->convs1[ci], v->convs2[ci], v->acts[ai], v->acts[ai + 1], cur, to_next ? bf.nx : (void*)bf.xs,
+                          to_next ? 1 : 0, j > 0 ? bf.xs : nullptr, 1.0f / v->nk, B, T, sj);
+            if (rc) return rc;
+            if (nb > 1 && j < v->nk - 1) BVG_CUDA(cudaEventRecord(v->ev_blk[j % 3], sj));
+          }
+          if (rc) return rc;
+          continue;
+        }
         if (!a1_ready) {
           rc = run_act(v, v->acts[ai], cur, BVG_F32, bf.a1[slot], adt, B, T, sj);
           if (rc) return rc;
@@ -991,6 +1037,15 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
     v->graphs.clear();
     if (!strcmp(key, "fuse_res")) v->opt_fuse_res = value; else v->fuse_res_min_kc = value;
   }
+  else if (!strcmp(key, "fuse_unit")) {
+    if (value != v->opt_fuse_unit) {
+      BVG_CUDA(cudaSetDevice(v->cfg.device));
+      BVG_CUDA(cudaDeviceSynchronize());
+      for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
+      v->graphs.clear();
+      v->opt_fuse_unit = value;
+    }
+  }
   else if (!strcmp(key, "fuse_act")) {
     if (value != v->opt_fuse_act) {
       BVG_CUDA(cudaSetDevice(v->cfg.device));
@@ -1032,8 +1087,8 @@ extern "C" int bvg_profile_dump(bvg_vocoder* v, const char* path) {
 }
 
 // Sums the CUDA-event durations recorded since the last read for one category
-// (0 tcgen05 conv, 1 SIMT conv, 2 fused activation, 3 other) and clears them when
-// category 3 (the last one) is read.  Synchronises the device.
+// (0 tcgen05 conv, 1 SIMT conv, 2 fused activation, 3 other, 4 whole AMP unit) and clears them when
+// category 3 is read (read it last).  Synchronises the device.
 extern "C" int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double* work, int* launches) {
   if (!v || category < 0 || category >= CAT_N || !ms || !work || !launches) BVG_FAIL(BVG_EINVAL, "bvg_profile_read: bad argument");
   BVG_CUDA(cudaSetDevice(v->cfg.device));
@@ -1045,7 +1100,7 @@ extern "C" int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double
     BVG_CUDA(cudaEventElapsedTime(&t, v->prof_ev[r.i0], v->prof_ev[r.i1]));
     *ms += t; *work += r.work; *launches += 1;
   }
-  if (category == CAT_N - 1) {
+  if (category == CAT_OTHER) {
     for (auto& e : v->prof_ev) v->ev_pool.push_back(e);
     v->prof_ev.clear();
     v->prof.clear();

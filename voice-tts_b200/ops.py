@@ -219,6 +219,47 @@ def _(x, weight, bias, res, alpha_log, beta_log, up_taps, down_taps, dilation, p
     return [x.new_empty(x.shape[0], weight.shape[0], x.shape[2]), x.new_empty(x.shape[0], weight.shape[0], x.shape[2])]
 
 
+@torch.library.custom_op("bvg_b200::amp_unit", mutates_args=())
+def amp_unit(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+             alpha1_log: torch.Tensor, beta1_log: torch.Tensor, alpha2_log: torch.Tensor, beta2_log: torch.Tensor,
+             up_taps: List[float], down_taps: List[float], accum: torch.Tensor, scale: float, out_bf16: bool,
+             dilation: int, precision: str, form: int) -> torch.Tensor:
+    """One iteration of AMPBlock1.forward (bigvgan.py:132-141): (x + c2(a2(c1(a1(x))))) * scale + accum on fp32 [B, C, T].
+    form: 0 = one kernel where the unit qualifies, 1 = layer by layer, 2 = one kernel or fail."""
+    _require_cuda(x, "x")
+    B, C, T = x.shape
+    k = w1.shape[-1]
+    if x.dtype != torch.float32 or tuple(w1.shape) != (C, C, k) or tuple(w2.shape) != (C, C, k):
+        raise RuntimeError("amp_unit: expects fp32 [B,C,T] and two weights [C,C,k]")
+    keep = []
+
+    def ptr(t, n):
+        if not t.numel():
+            return 0
+        if t.numel() != n:
+            raise RuntimeError("amp_unit: operand has %d elements, expected %d" % (t.numel(), n))
+        tt = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        keep.append(tt)
+        return tt.data_ptr()
+
+    args = [ptr(w1, C * C * k), ptr(b1, C), ptr(w2, C * C * k), ptr(b2, C), ptr(alpha1_log, C), ptr(beta1_log, C),
+            ptr(alpha2_log, C), ptr(beta2_log, C)]
+    aptr = ptr(accum, B * C * T)
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bvg_amp_unit_fwd(y.data_ptr(), x.data_ptr(), *args, _lib.taps_array(up_taps),
+                                          _lib.taps_array(down_taps), aptr, float(scale), int(out_bf16), B, C, T, k,
+                                          dilation, _mode(precision), int(form), _stream(x))
+    _lib.check(rc, "bvg_amp_unit_fwd")
+    return y
+
+
+@amp_unit.register_fake
+def _(x, w1, b1, w2, b2, alpha1_log, beta1_log, alpha2_log, beta2_log, up_taps, down_taps, accum, scale, out_bf16,
+      dilation, precision, form):
+    return torch.empty_like(x)
+
+
 @torch.library.custom_op("bvg_b200::conv_transpose1d", mutates_args=())
 def conv_transpose1d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, precision: str,
                      variant: int) -> torch.Tensor:
