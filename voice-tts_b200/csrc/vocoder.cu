@@ -479,7 +479,7 @@ static int run_body(bvg_vocoder* v, const Buffers& bf, int B, int T0, cudaStream
       for (int l = 0; l < v->nd; ++l) {
         const int ci = (i * v->nk + j) * v->nd + l;
         const int ai = (i * v->nk + j) * 2 * v->nd + 2 * l;
-        if (!a1_ready && can_fuse_unit(v, i, v->convs1[ci], v->convs2[ci], v->acts[ai], v->acts[ai + 1], cur, bf.y[slot], B, T)) {
+        if (!a1_ready && can_fuse_unit(v, i, v->convs1[ci], v->convs2[ci], v->acts[ai], v->acts[ai + 1], cur, bf.xs, B, T)) {
           if (l < v->nd - 1) {
             float* ynext = (l & 1) ? bf.y2[slot] : bf.y[slot];
             rc = run_unit(v, i, v->convs1[ci], v->convs2[ci], v->acts[ai], v->acts[ai + 1], cur, ynext, 0, nullptr, 1.f, B, T, sj);
