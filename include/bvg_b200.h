@@ -205,11 +205,9 @@ int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
  * "fuse_res" / "fuse_res_min_kc" (conv2 + residual + next activation in one kernel: 0 off, 1 when k*Cin >= min_kc,
  * 2 always), "fuse_unit" (1 [default]: whole AMP units of <= 96-channel stages as ONE kernel, bvg_amp_unit_fwd; 0: layer by
  * layer), "streams" (3 [default]: the AMP blocks of a stage on separate internal streams that fork from and join the caller's
- * stream; 1: serial; the result is bit-identical either way), "umma_variant" (debug).  Options that change the workspace layout drop captured graphs. */
+ * stream; 1: serial; the result is bit-identical either way), "conv_own_sm" (1 [default]: the persistent tcgen05 conv kernels request the whole shared-memory carve-out of their SM;
+ * 0: they leave room for one shared-memory-free block of another stream beside them).  Options that change what a forward enqueues drop captured graphs. */
 int bvg_set_option(bvg_vocoder* v, const char* key, int value);
-/* Debug only: filler kernel for co-residency experiments (mode 0: FMA spin, mode 1: streams `scratch`). */
-int bvg_debug_spin(int blocks, int threads, int iters, int mode, float* scratch, int64_t scratch_elems, bvg_stream_t stream);
-
 /* per-kernel CUDA-event timing (set option "profile"=1 first; disables graph replay while on):
  * category 0 = tcgen05 conv, 1 = SIMT conv, 2 = fused activation, 3 = other, 4 = whole AMP unit in one kernel
  * (work = the flops of its two convolutions).  Returns the summed

@@ -56,7 +56,6 @@ SYMBOLS = {
     "bvg_vocoder_fwd_host": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "bvg_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
     "bvg_last_forward_launches": (_i, [_vp]),
-    "bvg_debug_spin": (_i, [_i, _i, _i, _i, _vp, _i64, _vp]),
     "bvg_profile_dump": (_i, [_vp, ctypes.c_char_p]),
     "bvg_profile_read": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                               ctypes.POINTER(ctypes.c_int)]),

@@ -345,14 +345,6 @@ int bvg_amp_unit_fwd(float* dst, const float* x, const float* w1, const float* b
   return rc;
 }
 
-// Debug: a filler kernel for co-residency experiments (tools/coresident_probe.py): `blocks` x `threads` threads spin for
-// `iters` iterations; mode 0 = FMA only (no memory traffic), mode 1 = stream a scratch buffer through ld.global.cg / st.
-int bvg_debug_spin(int blocks, int threads, int iters, int mode, float* scratch, int64_t scratch_elems, bvg_stream_t stream) {
-  if (blocks <= 0 || threads <= 0 || threads > 1024) BVG_FAIL(BVG_EINVAL, "bvg_debug_spin: bad launch shape");
-  if (mode == 1 && (!scratch || scratch_elems <= 0)) BVG_FAIL(BVG_EINVAL, "bvg_debug_spin: mode 1 needs a scratch buffer");
-  return debug_spin_launch(blocks, threads, iters, mode, scratch, scratch_elems, (cudaStream_t)stream);
-}
-
 int bvg_create(const bvg_config* cfg, bvg_vocoder** out) { return vocoder_create(cfg, out); }
 int bvg_set_tensor(bvg_vocoder* v, const char* name, const float* data, int64_t numel, int is_device) {
   return vocoder_set_tensor(v, name, data, numel, is_device);

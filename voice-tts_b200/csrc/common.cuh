@@ -17,6 +17,20 @@
 // stale 128-byte lines per forward with __ldg, none with __ldcg).  L2 is the point of coherence.
 // Read-only parameters (weights, bias, alpha/beta, taps) keep __ldg.
 #define BVG_LDG(p) __ldcg(p)
+// experiment (co-residency corruption): stores of such tensors written straight to L2 as well
+#ifdef BVG_STG_CG
+#define BVG_STG(p, v) __stcg(p, v)
+#else
+#define BVG_STG(p, v) (*(p) = (v))
+#endif
+
+// experiment (co-residency corruption): a kernel whose st.global results the NEXT kernel of its stream reads through TMA
+// ends every thread with a gpu-scope fence and a generic->async proxy fence
+#ifdef BVG_EXIT_FENCE_ON
+#define BVG_EXIT_FENCE() do { __threadfence(); asm volatile("fence.proxy.async.global;" ::: "memory"); } while (0)
+#else
+#define BVG_EXIT_FENCE() do { } while (0)
+#endif
 
 namespace bvg {
 
@@ -51,6 +65,24 @@ extern std::atomic<uint64_t> g_launches;
   } while (0)
 
 int ensure_device_ok();  // BVG_OK if the current device is sm_100 (cached)
+
+// Entry points that work on a handle make its device current and put the caller's device back on return: a process
+// that drives several GPUs must not find torch.cuda.current_device() changed by a call into this library.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    else prev = -1;   // nothing to restore
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define BVG_DEVICE(dev)                                                          \
+  ::bvg::DeviceGuard _dg(dev);                                                   \
+  if (!_dg.ok) BVG_FAIL(BVG_ENODEV, "cannot make device %d current", (int)(dev))
 
 struct Taps {
   float up[12];    // up-filter taps already multiplied by the x2 gain
@@ -311,6 +343,27 @@ __device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t& r0, uint3
 }
 __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r0) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
+}
+// `tcgen05.wait::ld` compiles to NO instruction that blocks (SASS: WARPSYNC + NOP; measured on sm_100a, CUDA 12.9): ptxas
+// enforces completion of a TMEM load - like that of any other load - only through the scoreboard wait of the first
+// instruction that READS a destination register.  A hand-off that must follow the completion of loads whose values have
+// not been used yet (release of a TMEM accumulator to the MMA warp, release of a shared-memory slot to a TMA producer)
+// therefore first passes the registers through one of these empty asm statements: they count as a read, so the
+// scoreboard wait lands in front of the hand-off.  Without it, an mbarrier arrive can overtake loads still queued in a
+// stalled load pipeline - the round-1 "co-residency" corruption.
+__device__ __forceinline__ void consume16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+}
+__device__ __forceinline__ void consume8(uint32_t (&r)[8]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+}
+__device__ __forceinline__ void consume16f(float (&r)[16]) {
+  asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]),
+               "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15])::"memory");
+}
+__device__ __forceinline__ void consume8f(float (&r)[8]) {
+  asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7])::"memory");
 }
 // wait for this thread's TMEM loads; the registers ride through the asm so that no use of them can be
 // scheduled above the wait

@@ -25,6 +25,7 @@ struct ConvArgs {
   int Cout_r;   // rows of Wp per tap (multiple of 128)
   int out_ld;   // row pitch of out/res/accum in elements
   int k, dil;
+  int own_sm = 1;   // tcgen05 kernels: 1 = request the SM's whole shared-memory carve-out (no co-resident blocks), 0 = only what is used
 };
 
 int conv_simt_launch(const ConvArgs& a, cudaStream_t st);
@@ -85,7 +86,6 @@ int btc_pad_cast(void* dst, int out_dtype, const float* src, int64_t rows, int C
 int conv_post_launch(void* dst, int out_i16, const void* src, int in_dtype, const float* w, float bias, int B,
                      int Cp, int64_t T, int use_tanh, cudaStream_t st);
 int f32_to_i16(int16_t* dst, const float* src, int64_t n, cudaStream_t st);
-int debug_spin_launch(int blocks, int threads, int iters, int mode, float* scratch, int64_t n, cudaStream_t st);
 
 // channel padding of the channels-last tensors (the tcgen05 kernels accept multiples of 8 - the zero fill of their
 // 64-channel TMA boxes completes the last K step - but 16 keeps every bf16 row a multiple of 32 bytes)

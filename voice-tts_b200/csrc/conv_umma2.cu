@@ -32,8 +32,6 @@
 // CTA-wide barrier in the steady state and no per-thread global memory access.
 //
 // reference semantics: torch Conv1d/ConvTranspose1d as built in bigvgan.py:59-66,76-83,285-287,306-312.
-#include <cstdlib>
-
 #include "umma_common.cuh"
 
 namespace bvg {
@@ -73,7 +71,6 @@ struct U2Params {
   int a_stages;
   int w_resident;    // all k*nchunks weight tiles are loaded once and stay in the ring slots
   int CB;            // time rows per epilogue block = NCOL * 2 * rep
-  long long* dbg;    // optional per-role wait-cycle counters of CTA 0 (BVG_U2_DBG=1)
 };
 
 struct U2Tile {
@@ -90,19 +87,6 @@ __device__ __forceinline__ U2Tile u2_tile(const U2Params& p, int64_t tile) {
   if (t.nb_end > p.NT) t.nb_end = p.NT;
   return t;
 }
-
-// mbarrier wait that optionally accumulates the cycles spent waiting (debug instrumentation)
-__device__ __forceinline__ void u2_wait(uint64_t* bar, uint32_t parity, bool dbg, long long& cnt) {
-  if (dbg) {
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    cnt += clock64() - t0;
-  } else {
-    mbar_wait(bar, parity);
-  }
-}
-enum { U2D_TOTAL = 0, U2D_X_EMPTY, U2D_A_EMPTY0, U2D_A_EMPTY1, U2D_MMA_TEMPTY, U2D_MMA_XFULL, U2D_MMA_AFULL, U2D_EPI_TFULL,
-       U2D_EPI_INFULL, U2D_EPI_OUTFREE, U2D_ST_READY, U2D_ST_READ, U2D_IN_FREE, U2D_N };
 
 // NIN: 0 = plain, 1 = + residual, 2 = + residual and accumulate operand
 template <int NIN, bool BF16OUT>
@@ -154,9 +138,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int CB = p.CB, CW = p.CW;
-  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
-  long long w0 = 0, w1 = 0, w2 = 0;
-  const long long t_start = dbg ? clock64() : 0;
 
   if (warp == 0) {
     {
@@ -167,7 +148,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const U2Tile t = u2_tile(p, tile);
         const int trow = t.t0 - p.center * p.dil;
         for (int c = 0; c < p.nchunks; ++c) {
-          u2_wait(&x_empty[xs], xph ^ 1, dbg, w0);
+          mbar_wait(&x_empty[xs], xph ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&x_full[xs], (uint32_t)p.x_nbox * xbox_bytes);
             unsigned char* dstx = x_st + xs * U2_X_STAGE_BYTES;
@@ -178,7 +159,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           if (++xs == U2_X_STAGES) { xs = 0; xph ^= 1; }
         }
       }
-      if (dbg && lane == 0) p.dbg[U2D_X_EMPTY] = w0;
     }
   } else if (warp == 10 || warp == 11) {
     {
@@ -192,7 +172,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int c = 0; c < p.nchunks; ++c) {
           for (int j = 0; j < p.k; ++j, ++n) {
             if ((n & 1u) == mine) {
-              u2_wait(&a_empty[as], aph ^ 1, dbg, w0);
+              mbar_wait(&a_empty[as], aph ^ 1);
               if (elect_one()) {
                 mbar_expect_tx(&a_full[as], a_bytes);
                 tma_load_3d(a_st + as * U2_SLOT_BYTES, &tmap_w, c * 64, cot * CW, j, &a_full[as]);
@@ -203,7 +183,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
-      if (dbg && lane == 0) p.dbg[U2D_A_EMPTY0 + mine] = w0;
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer: the whole warp walks the (warp-uniform) loops so that
@@ -224,19 +203,19 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const bool w_wait = !resident || tile == (int64_t)blockIdx.x;
         if (resident) as = 0;
-        u2_wait(&t_empty[acc], accph ^ 1, dbg, w0);
+        mbar_wait(&t_empty[acc], accph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256u;
         uint32_t accum = 0;
         for (int c = 0; c < p.nchunks; ++c) {
           int nkk = (p.Cin_p - c * 64 + 15) >> 4;      // K steps that hold real channels
           nkk = nkk > 4 ? 4 : nkk;
-          u2_wait(&x_full[xs], xph, dbg, w1);
+          mbar_wait(&x_full[xs], xph);
           tc_fence_after();
           uint32_t b_lo = x_lo0 + xs * (uint32_t)(U2_X_STAGE_BYTES >> 4);
           for (int j = 0; j < k; ++j, b_lo += tap_step) {
             if (w_wait) {
-              u2_wait(&a_full[as], aph, dbg, w2);
+              mbar_wait(&a_full[as], aph);
               tc_fence_after();
             }
             const uint32_t a_lo = a_lo0 + as * (uint32_t)(U2_SLOT_BYTES >> 4);
@@ -258,7 +237,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         __syncwarp();
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
-      if (dbg && lane == 0) { p.dbg[U2D_MMA_TEMPTY] = w0; p.dbg[U2D_MMA_XFULL] = w1; p.dbg[U2D_MMA_AFULL] = w2; }
     }
   } else if (warp == 12) {
     {
@@ -271,15 +249,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int nb = 0; nb < t.nb_end; nb += CB, ++cb) {
           const uint32_t ob = cb & 1u;
           if (cb >= 1) {                       // hand the previous block's buffer back as soon as it has been read
-            const long long tr = dbg ? clock64() : 0;
             if (elect_one()) {
               bulk_wait_group_read<0>();
               mbar_arrive(&out_free[ob ^ 1u]);
             }
             __syncwarp();
-            if (dbg) w1 += clock64() - tr;
           }
-          u2_wait(&out_ready[ob], (cb >> 1) & 1u, dbg, w0);
+          mbar_wait(&out_ready[ob], (cb >> 1) & 1u);
           if (elect_one()) {
             tma_store_3d(&tmap_out, out_st + ob * U2_SLOT_BYTES, t.cot * CW, t.t0 + nb, t.b);
             bulk_commit_group();
@@ -289,7 +265,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       __syncwarp();
       if (elect_one()) bulk_wait_group<0>();
-      if (dbg && lane == 0) { p.dbg[U2D_ST_READY] = w0; p.dbg[U2D_ST_READ] = w1; }
     }
   } else if (warp == 13) {
     if (NIN >= 1) {
@@ -300,7 +275,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const U2Tile t = u2_tile(p, tile);
         for (int nb = 0; nb < t.nb_end; nb += CB, ++cb) {
           const uint32_t slot = cb % U2_IN_SLOTS;
-          u2_wait(&in_free[slot], ((cb / U2_IN_SLOTS) & 1u) ^ 1u, dbg, w0);
+          mbar_wait(&in_free[slot], ((cb / U2_IN_SLOTS) & 1u) ^ 1u);
           if (elect_one()) {
             unsigned char* dst = in_st + slot * U2_SLOT_BYTES;
             mbar_expect_tx(&in_full[slot], in_bytes);
@@ -310,7 +285,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           __syncwarp();
         }
       }
-      if (dbg && lane == 0) p.dbg[U2D_IN_FREE] = w0;
     }
   } else {
     // ------------------------------------------------ epilogue math warps 2..9
@@ -334,7 +308,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const U2Tile t = u2_tile(p, tile);
       const float bv = (p.bias && lane_ok) ? BVG_LDG(p.bias + (int64_t)t.b * p.bias_bs + t.cot * CW + ch) : 0.f;
 
-      u2_wait(&t_full[acc], accph, dbg, w0);
+      mbar_wait(&t_full[acc], accph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * 256u + (uint32_t)colbase;
       for (int nb = 0; nb < t.nb_end; nb += CB, ++cb) {
@@ -346,7 +320,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         float rv[NCOL], av[NCOL];
         if (NIN >= 1) {
-          u2_wait(&in_full[slot], (cb / U2_IN_SLOTS) & 1u, dbg, w1);
+          mbar_wait(&in_full[slot], (cb / U2_IN_SLOTS) & 1u);
           if (lane_ok) {
             const uint32_t ia = in_base + slot * U2_SLOT_BYTES;
 #pragma unroll
@@ -355,17 +329,26 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
               for (int i = 0; i < NCOL; ++i) av[i] = ld_shared_f32(ia + acc_off + i * istep);
             }
+            // the loads above are only ISSUED at this point: wait until their values are in registers (common.cuh,
+            // consume16) before the slot is handed back to the TMA producer - an arrive that overtook loads still queued
+            // in a stalled LSU let the refill overwrite rows this warp had not read yet
+            if (NCOL == 16) consume16f(reinterpret_cast<float(&)[16]>(rv)); else consume8f(reinterpret_cast<float(&)[8]>(rv));
+            if (NIN == 2) { if (NCOL == 16) consume16f(reinterpret_cast<float(&)[16]>(av)); else consume8f(reinterpret_cast<float(&)[8]>(av)); }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&in_free[slot]);   // values are in registers: the slot may be refilled
         }
-        if (warp_ok) tmem_ld_wait();
+        if (warp_ok) {
+          // same for the accumulator columns before the accumulator can be handed back to the MMA warp below
+          tmem_ld_wait();
+          if (NCOL == 16) consume16(reinterpret_cast<uint32_t(&)[16]>(v)); else consume8(reinterpret_cast<uint32_t(&)[8]>(v));
+        }
         if (nb + CB >= t.nb_end) {           // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[acc]);
         }
-        u2_wait(&out_free[ob], ((cb >> 1) & 1u) ^ 1u, dbg, w2);
+        mbar_wait(&out_free[ob], ((cb >> 1) & 1u) ^ 1u);
         if (lane_ok) {
           const uint32_t oa = out_base + ob * U2_SLOT_BYTES;
 #pragma unroll
@@ -384,12 +367,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
-    if (dbg && threadIdx.x == 64) { p.dbg[U2D_EPI_TFULL] = w0; p.dbg[U2D_EPI_INFULL] = w1; p.dbg[U2D_EPI_OUTFREE] = w2; }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (dbg && threadIdx.x == 0) p.dbg[U2D_TOTAL] = clock64() - t_start;
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -495,18 +476,11 @@ int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   }
   const int sms = umma_sm_count();
   const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
-  static const bool want_dbg = getenv("BVG_U2_DBG") != nullptr;
-  static long long* dbg_buf = nullptr;
-  p.dbg = nullptr;
-  if (want_dbg) {
-    if (!dbg_buf) BVG_CUDA(cudaMalloc((void**)&dbg_buf, U2D_N * sizeof(long long)));
-    BVG_CUDA(cudaMemsetAsync(dbg_buf, 0, U2D_N * sizeof(long long), st));
-    p.dbg = dbg_buf;
-  }
+  const int smem = a.own_sm ? U2_SMEM_BYTES : U2_SMEM_USED;
 #define BVG_U2_LAUNCH(N, O)                                                                                          \
   do {                                                                                                               \
     BVG_CUDA(cudaFuncSetAttribute(conv_umma2_kernel<N, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES)); \
-    conv_umma2_kernel<N, O><<<grid, U2_THREADS, U2_SMEM_BYTES, st>>>(mx, mw, mo, mr, ma, p);                         \
+    conv_umma2_kernel<N, O><<<grid, U2_THREADS, smem, st>>>(mx, mw, mo, mr, ma, p);                         \
   } while (0)
   const bool ob = a.out_dtype == BVG_BF16;
   if (nin == 0) { if (ob) BVG_U2_LAUNCH(0, true); else BVG_U2_LAUNCH(0, false); }
@@ -514,20 +488,6 @@ int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   else { if (ob) BVG_U2_LAUNCH(2, true); else BVG_U2_LAUNCH(2, false); }
 #undef BVG_U2_LAUNCH
   BVG_LAUNCHED();
-  if (want_dbg) {
-    long long h[U2D_N];
-    BVG_CUDA(cudaStreamSynchronize(st));
-    BVG_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-    const long long tiles0 = (p.n_tiles + grid - 1) / grid;
-    fprintf(stderr,
-            "u2dbg Cin=%d CW=%d ncot=%d k=%d dil=%d nin=%d bf16=%d NT=%d res=%d tiles/cta=%lld | total %lld (%.0f/tile) | Xprod wait x_empty %lld | "
-            "W wait a_empty %lld %lld | MMA wait t_empty %lld x_full %lld a_full %lld | EPI wait t_full %lld in_full %lld out_free %lld | "
-            "ST wait ready %lld read %lld | IN wait free %lld\n",
-            a.Cin_p, p.CW, p.n_cotiles, a.k, a.dil, nin, (int)ob, p.NT, p.w_resident, tiles0, h[U2D_TOTAL],
-            (double)h[U2D_TOTAL] / (double)tiles0, h[U2D_X_EMPTY], h[U2D_A_EMPTY0], h[U2D_A_EMPTY1], h[U2D_MMA_TEMPTY],
-            h[U2D_MMA_XFULL], h[U2D_MMA_AFULL], h[U2D_EPI_TFULL], h[U2D_EPI_INFULL], h[U2D_EPI_OUTFREE], h[U2D_ST_READY],
-            h[U2D_ST_READ], h[U2D_IN_FREE]);
-  }
   return BVG_OK;
 }
 

@@ -569,12 +569,13 @@ int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* b
   }
   const int sms = umma_sm_count();
   const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
+  const int smem = a.own_sm ? UA_SMEM_BYTES : UA_SMEM_USED;
   if (a.res) {
     BVG_CUDA(cudaFuncSetAttribute(conv_umma2a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES));
-    conv_umma2a_kernel<true><<<grid, UA_THREADS, UA_SMEM_BYTES, st>>>(mx, mw, mo, mt, p);
+    conv_umma2a_kernel<true><<<grid, UA_THREADS, smem, st>>>(mx, mw, mo, mt, p);
   } else {
     BVG_CUDA(cudaFuncSetAttribute(conv_umma2a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES));
-    conv_umma2a_kernel<false><<<grid, UA_THREADS, UA_SMEM_BYTES, st>>>(mx, mw, mo, mt, p);
+    conv_umma2a_kernel<false><<<grid, UA_THREADS, smem, st>>>(mx, mw, mo, mt, p);
   }
   BVG_LAUNCHED();
   return BVG_OK;

@@ -414,29 +414,5 @@ int split3_f32(float* o0, float* o1, float* o2, const float* src, int64_t n, cud
   return BVG_OK;
 }
 
-// ---- debug filler kernel (co-residency experiments) ------------------------------------------------------------
-__global__ void debug_spin_kernel(int iters, int mode, float* scratch, int64_t n) {
-  float a = 1.0f + threadIdx.x * 1e-6f, b = 0.5f, c = 0.25f, d = 0.125f;
-  if (mode == 0) {
-    for (int i = 0; i < iters; ++i) {
-      a = fmaf(a, 0.999999f, 1e-7f); b = fmaf(b, 0.999998f, 2e-7f); c = fmaf(c, 0.999997f, 3e-7f); d = fmaf(d, 0.999996f, 4e-7f);
-    }
-    if (a + b + c + d == 123456.0f && scratch) scratch[0] = a;
-  } else {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int i = 0; i < iters; ++i) {
-      const int64_t j = idx % n;
-      const float v = __ldcg(scratch + j);
-      scratch[j] = fmaf(v, 0.999999f, 1e-7f);
-      idx += stride;
-    }
-  }
-}
-int debug_spin_launch(int blocks, int threads, int iters, int mode, float* scratch, int64_t n, cudaStream_t st) {
-  debug_spin_kernel<<<blocks, threads, 0, st>>>(iters, mode, scratch, n);
-  BVG_LAUNCHED();
-  return BVG_OK;
-}
 
 }  // namespace bvg

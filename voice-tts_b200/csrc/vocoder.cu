@@ -72,12 +72,14 @@ struct bvg_vocoder {
   bool has_post_w = false, has_post_b = false;
   bool finalized = false;
   // options
-  int opt_graph = 0, opt_conv_impl = 0, opt_umma_variant = 0, opt_fast_sin = -1;
+  int opt_graph = 0, opt_conv_impl = 0, opt_fast_sin = -1;
+  int opt_own_sm = 1;              // persistent tcgen05 conv CTAs take their SM's whole shared-memory carve-out (ConvArgs::own_sm)
   int opt_split_terms = 3;         // fp32 storage + tensor cores (conv_impl = 3): term pairs per convolution (3, 6 or 9)
   int opt_fuse_res = 1;            // conv2 of an AMP unit adds the residual AND applies the next unit's first activation (bf16 mode)
   int opt_fuse_act = 1;            // conv1 of an AMP unit applies the following activation in its epilogue (bf16 mode)
   int fuse_res_min_kc = 4096;      // smallest k * Cin whose conv2 takes the fused residual + activation epilogue
-  int opt_fuse_unit = 1;           // whole AMP units of <= 96-channel stages as one kernel (amp_unit.cu; bf16 mode)
+  int opt_fuse_unit = 0;           // 1: whole AMP units of <= 96-channel stages as one kernel (amp_unit.cu; bf16 mode) - measured slower
+                                   // than the layer-by-layer path on B200, so off by default
   int opt_streams = 3;             // AMP blocks of one stage run on up to this many streams (1 = serial); see DESIGN.md 8.5
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // internal streams for AMP blocks 0 .. nk-2
   cudaEvent_t ev_fork = nullptr, ev_blk[3] = {nullptr, nullptr, nullptr};
@@ -273,8 +275,9 @@ static inline void prof_break(bvg_vocoder* v) { v->prof_last = -1; }
 // 478 audio-s/s against 147-223 for the SIMT kernels (first / second generation) and 4 000 for plain bf16 (41 dB).
 struct SplitPlan { ConvArgs first, mid, last; };
 static bool plan_conv_split(const ConvW& c, void* out, int out_dt, const float* res, const float* accum, float scale, int B,
-                            int64_t T, const float* bias, int64_t bias_bs, void* const sp[3], float* t, SplitPlan* pl) {
+                            int64_t T, const float* bias, int64_t bias_bs, void* const sp[3], float* t, SplitPlan* pl, int own_sm) {
   ConvArgs a;
+  a.own_sm = own_sm;
   a.in = sp[0]; a.w = c.ws[0]; a.bias = nullptr; a.out = t; a.res = res; a.accum = nullptr; a.scale = 1.f;
   a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_F32;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
@@ -299,10 +302,128 @@ static int run_conv_split(bvg_vocoder* v, const ConvW& c, const float* in, Split
     ConvArgs& p = q == q0 ? pl.first : (q == 8 ? pl.last : pl.mid);
     p.in = sp[order[q][0]];
     p.w = c.ws[order[q][1]];
-    if ((rc = conv_umma_launch(p, v->opt_umma_variant, st))) return rc;
+    if ((rc = conv_umma_launch(p, 0, st))) return rc;
   }
   return BVG_OK;
 }
+
+#ifdef BVG_DUAL
+// Debug builds only (BVG_EXTRA_FLAGS=-DBVG_DUAL, never in libbvg_b200.so): every activation / convolution launch runs a
+// second time into a scratch buffer on the same stream and a compare kernel counts the words that differ - a kernel whose
+// result depends on what else is resident on its SMs shows up as a non-zero counter of ITS launch record (tools/soak_dual.py).
+struct DualLog { long long idx; float a, b; float r[7]; int tag; int pad; };
+__device__ DualLog g_dual_log[256];
+__device__ unsigned int g_dual_nlog;
+__global__ void dual_cmp_kernel(const uint32_t* a, const uint32_t* b, long long n, unsigned int* slot, const float* res,
+                                long long blk, int tag) {
+  unsigned int d = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (a[i] != b[i]) {
+      ++d;
+      const unsigned int k = atomicAdd(&g_dual_nlog, 1u);
+      if (k < 256) {
+        DualLog e;
+        e.idx = i; e.a = __uint_as_float(a[i]); e.b = __uint_as_float(b[i]); e.tag = tag; e.pad = 0;
+        for (int q = 0; q < 7; ++q) {
+          const long long j = i + (long long)(q - 3) * blk;
+          e.r[q] = (res && j >= 0 && j < n) ? res[j] : 0.f;
+        }
+        g_dual_log[k] = e;
+      }
+    }
+  }
+  if (d) atomicAdd(slot, d);
+}
+static unsigned int* g_dual = nullptr;
+static int g_dual_n = 0;
+static int g_dual_tags[8192];
+static void* g_dual_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+static cudaStream_t g_dual_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+static const size_t kDualBytes = (size_t)96 << 20;
+static void* dual_scratch(cudaStream_t st, size_t bytes) {
+  if (bytes > kDualBytes) return nullptr;
+  for (int i = 0; i < 4; ++i) {
+    if (g_dual_scratch[i] && g_dual_streams[i] == st) return g_dual_scratch[i];
+    if (!g_dual_scratch[i]) {
+      if (cudaMalloc(&g_dual_scratch[i], kDualBytes) != cudaSuccess) return nullptr;
+      g_dual_streams[i] = st;
+      return g_dual_scratch[i];
+    }
+  }
+  return nullptr;
+}
+static void dual_check(cudaStream_t st, const void* a, const void* b, size_t bytes, int tag, const float* res = nullptr,
+                       long long blk = 0) {
+  if (!g_dual || g_dual_n >= 8192) return;
+  g_dual_tags[g_dual_n] = tag;
+  dual_cmp_kernel<<<148, 256, 0, st>>>((const uint32_t*)a, (const uint32_t*)b, (long long)(bytes / 4), g_dual + g_dual_n, res, blk, tag);
+  ++g_dual_n;
+}
+extern "C" int bvg_dual_log(void* out, int max) {
+  cudaDeviceSynchronize();
+  unsigned int n = 0;
+  cudaMemcpyFromSymbol(&n, g_dual_nlog, sizeof(n));
+  if (n > 256) n = 256;
+  if ((int)n > max) n = max;
+  cudaMemcpyFromSymbol(out, g_dual_log, n * sizeof(DualLog));
+  unsigned int z = 0;
+  cudaMemcpyToSymbol(g_dual_nlog, &z, sizeof(z));
+  return (int)n;
+}
+extern "C" int bvg_dual_begin() {
+  if (!g_dual) cudaMalloc((void**)&g_dual, 8192 * sizeof(unsigned int));
+  cudaDeviceSynchronize();
+  cudaMemset(g_dual, 0, 8192 * sizeof(unsigned int));
+  g_dual_n = 0;
+  return 0;
+}
+extern "C" int bvg_dual_read(unsigned int* counts, int* tags, int max) {
+  cudaDeviceSynchronize();
+  const int n = g_dual_n < max ? g_dual_n : max;
+  cudaMemcpy(counts, g_dual, n * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < n; ++i) tags[i] = g_dual_tags[i];
+  return n;
+}
+#endif
+
+#ifdef BVG_TRACE
+// Debug builds only (BVG_EXTRA_FLAGS=-DBVG_TRACE, never in libbvg_b200.so): a position-weighted checksum of every tensor a
+// forward writes, taken on the writing stream right behind the kernel, to find the first launch whose result differs
+// between two schedules (tools/soak_trace.py).
+__global__ void trace_sum_kernel(const uint32_t* p, long long n, unsigned long long* slot) {
+  unsigned long long s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += (unsigned long long)p[i] * (unsigned long long)((i % 8191) + 1);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(slot, s);
+}
+static unsigned long long* g_trace = nullptr;
+static int g_trace_n = 0;
+static int g_trace_tags[8192];
+static void trace_out(cudaStream_t st, const void* p, size_t bytes, int tag) {
+  if (!g_trace || g_trace_n >= 8192) return;
+  g_trace_tags[g_trace_n] = tag;
+  trace_sum_kernel<<<296, 256, 0, st>>>((const uint32_t*)p, (long long)(bytes / 4), g_trace + g_trace_n);
+  ++g_trace_n;
+}
+extern "C" int bvg_trace_begin() {
+  if (!g_trace) cudaMalloc((void**)&g_trace, 8192 * sizeof(unsigned long long));
+  cudaDeviceSynchronize();
+  cudaMemset(g_trace, 0, 8192 * sizeof(unsigned long long));
+  g_trace_n = 0;
+  return 0;
+}
+extern "C" int bvg_trace_read(unsigned long long* sums, int* tags, int max) {
+  cudaDeviceSynchronize();
+  const int n = g_trace_n < max ? g_trace_n : max;
+  cudaMemcpy(sums, g_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < n; ++i) tags[i] = g_trace_tags[i];
+  return n;
+}
+#define BVG_TRACE_OUT(st, p, bytes, tag) trace_out(st, p, bytes, tag)
+#else
+#define BVG_TRACE_OUT(st, p, bytes, tag)
+#endif
 
 static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, void* out, int out_dt,
                     const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st,
@@ -312,11 +433,11 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
   if (bias_rows) { a.bias = bias_rows; a.bias_bs = c.Cout_r; }   // per-utterance rows: layer bias + cond(speaker_embedding)
   a.in_dtype = in_dt; a.w_dtype = v->act_dt; a.out_dtype = out_dt;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
-  a.k = c.k; a.dil = c.dil;
+  a.k = c.k; a.dil = c.dil; a.own_sm = v->opt_own_sm;
   if (v->cfg.mode == BVG_MODE_FP32 && v->opt_conv_impl == 3 && in_dt == BVG_F32 && sp && t && c.ws[0]) {
     void* const spl[3] = {sp[0], sp[1], sp[2]};
     SplitPlan pl;
-    if (plan_conv_split(c, out, out_dt, res, accum, scale, B, T, a.bias, a.bias_bs, spl, t, &pl)) {
+    if (plan_conv_split(c, out, out_dt, res, accum, scale, B, T, a.bias, a.bias_bs, spl, t, &pl, v->opt_own_sm)) {
       ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
       ps.cin = c.Cin; ps.cout = c.up > 0 ? -c.Cout : c.Cout; ps.k = c.k_torch; ps.dil = 300 + c.dil; ps.rows = (long long)B * T;
       return run_conv_split(v, c, (const float*)in, pl, B, T, st, spl);
@@ -330,7 +451,25 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
   // algorithmic flops: 2*Cout*Cin*k*T_out*B (Conv1d) / 2*Cin*Cout*k*T_in*B (ConvTranspose1d), unpadded channels
   ProfScope ps(v, st, umma ? CAT_CONV_UMMA : CAT_CONV_SIMT, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   ps.cin = c.Cin; ps.cout = c.up > 0 ? -c.Cout : c.Cout; ps.k = c.k_torch; ps.dil = c.dil; ps.rows = (long long)B * T;
-  return umma ? conv_umma_launch(a, v->opt_umma_variant, st) : conv_simt_launch(a, st);
+  const int rc_ = umma ? conv_umma_launch(a, 0, st) : conv_simt_launch(a, st);
+#ifdef BVG_DUAL
+  if (!rc_ && umma && out != (const void*)res && out != (const void*)accum) {
+    const size_t nb_ = (size_t)B * T * c.Cout_n * dtype_size(out_dt);
+    void* sc_ = dual_scratch(st, nb_);
+    if (sc_) {
+      ConvArgs a2_ = a;
+      a2_.out = sc_;
+      conv_umma_launch(a2_, 0, st);
+      {
+        const int rep_ = c.Cout_n <= 32 ? 4 : (c.Cout_n <= 64 ? 2 : 1);
+        dual_check(st, out, sc_, nb_, 1000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil, out_dt == BVG_F32 ? res : nullptr,
+                   (long long)(accum ? 16 : 32) * rep_ * c.Cout_n);
+      }
+    }
+  }
+#endif
+  BVG_TRACE_OUT(st, out, (size_t)B * T * c.Cout_n * dtype_size(out_dt), 1000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
+  return rc_;
 }
 
 // c1 followed by a2 of one AMP unit (bigvgan.py:136-138) as ONE launch when the fused kernel takes the layer
@@ -344,7 +483,7 @@ static bool can_fuse_conv_act(const bvg_vocoder* v, const ConvW& c, const void* 
   a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = nullptr; a.accum = nullptr; a.scale = 1.f;
   a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
-  a.k = c.k; a.dil = c.dil;
+  a.k = c.k; a.dil = c.dil; a.own_sm = v->opt_own_sm;
   return conv_act_fused_supported(a);
 }
 static int run_conv_act(bvg_vocoder* v, const ConvW& c, const ActW& act, const void* in, void* out, int B, int64_t T,
@@ -353,11 +492,25 @@ static int run_conv_act(bvg_vocoder* v, const ConvW& c, const ActW& act, const v
   a.in = in; a.w = c.w; a.bias = c.bias; a.out = out; a.res = nullptr; a.accum = nullptr; a.scale = 1.f;
   a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
-  a.k = c.k; a.dil = c.dil;
+  a.k = c.k; a.dil = c.dil; a.own_sm = v->opt_own_sm;
   // accounted as a conv launch: algorithmic conv flops; the fused activation's algorithmic bytes are zero by construction
   ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   ps.cin = c.Cin; ps.cout = c.Cout; ps.k = c.k_torch; ps.dil = 100 + c.dil; ps.rows = (long long)B * T;
-  return conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st);
+  const int rc_ = conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st);
+#ifdef BVG_DUAL
+  if (!rc_) {
+    const size_t nb_ = (size_t)B * T * c.Cout_n * 2;
+    void* sc_ = dual_scratch(st, nb_);
+    if (sc_) {
+      ConvArgs a2_ = a;
+      a2_.out = sc_;
+      conv_act_fused_launch(a2_, act.alpha, act.beta, act.taps, st);
+      dual_check(st, out, sc_, nb_, 2000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
+    }
+  }
+#endif
+  BVG_TRACE_OUT(st, out, (size_t)B * T * c.Cout_n * 2, 2000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
+  return rc_;
 }
 
 // c2 + residual of unit l and a1 of unit l+1 (bigvgan.py:139 `x = xt + x`, then :134 of the next iteration) as ONE launch:
@@ -373,7 +526,7 @@ static bool can_fuse_conv_res_act(const bvg_vocoder* v, const ConvW& c, const vo
   a.in = in; a.w = c.w; a.bias = c.bias; a.out = a_out; a.res = res; a.accum = nullptr; a.scale = 1.f;
   a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
-  a.k = c.k; a.dil = c.dil;
+  a.k = c.k; a.dil = c.dil; a.own_sm = v->opt_own_sm;
   return conv_act_fused_supported(a);
 }
 static int run_conv_res_act(bvg_vocoder* v, const ConvW& c, const ActW& act, const void* in, void* a_out, const float* res,
@@ -382,10 +535,13 @@ static int run_conv_res_act(bvg_vocoder* v, const ConvW& c, const ActW& act, con
   a.in = in; a.w = c.w; a.bias = c.bias; a.out = a_out; a.res = res; a.accum = nullptr; a.scale = 1.f;
   a.in_dtype = BVG_BF16; a.w_dtype = BVG_BF16; a.out_dtype = BVG_BF16;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
-  a.k = c.k; a.dil = c.dil;
+  a.k = c.k; a.dil = c.dil; a.own_sm = v->opt_own_sm;
   ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   ps.cin = c.Cin; ps.cout = c.Cout; ps.k = c.k_torch; ps.dil = 200 + c.dil; ps.rows = (long long)B * T;
-  return conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st, y_out);
+  const int rc_ = conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st, y_out);
+  BVG_TRACE_OUT(st, a_out, (size_t)B * T * c.Cout_n * 2, 3000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
+  BVG_TRACE_OUT(st, y_out, (size_t)B * T * c.Cout_n * 4, 3500000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
+  return rc_;
 }
 
 static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, void* out, int out_dt, int B,
@@ -398,7 +554,20 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   // the thread of the last real pair also stores exact zeros into the pad channels, which the zero weight columns of the
   // next conv need (a stale NaN bit pattern times 0 would poison the accumulator).  Saves a quarter of that stage's work.
   const int Cact = (a.Cp == a.C + 8 && !(a.C & 1) && T >= 64) ? a.C : a.Cp;   // (short sequences: all-scalar launch, all channels)
-  return act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
+  const int rc_ = act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
+#ifdef BVG_DUAL
+  if (!rc_) {
+    const size_t nb_ = (size_t)B * T * a.Cp * dtype_size(out_dt);
+    void* sc_ = dual_scratch(st, nb_);
+    if (sc_) {
+      cudaMemcpyAsync(sc_, out, nb_, cudaMemcpyDeviceToDevice, st);   // pad channels the kernel does not write
+      act1d_cl_launch(sc_, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
+      dual_check(st, out, sc_, nb_, 4000000 + a.C * 1000 + (int)dtype_size(in_dt));
+    }
+  }
+#endif
+  BVG_TRACE_OUT(st, out, (size_t)B * T * a.Cp * dtype_size(out_dt), 4000000 + a.C * 1000 + (int)dtype_size(in_dt));
+  return rc_;
 }
 
 // One whole AMP unit (a1 -> c1 -> a2 -> c2 + residual, bigvgan.py:132-141) as ONE launch for the narrow stages
@@ -621,7 +790,7 @@ int vocoder_forward(bvg_vocoder* v, const float* mel, const float* emb, void* wa
   if (B == 0 || T0 == 0) return BVG_OK;
   if (!mel || !wav) BVG_FAIL(BVG_EINVAL, "null mel/wav pointer");
   if ((int64_t)T0 * v->total_up > 0x3fffffffLL) BVG_FAIL(BVG_EINVAL, "utterance too long");
-  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  BVG_DEVICE(v->cfg.device);
   int rc = ensure_device_ok();
   if (rc) return rc;
   const uint64_t l0 = g_launches.load();
@@ -644,8 +813,11 @@ int vocoder_forward(bvg_vocoder* v, const float* mel, const float* emb, void* wa
 // ------------------------------------------------------------------ weights ----
 static bool parse_int(const char*& s, int* out) {
   if (*s < '0' || *s > '9') return false;
-  int v = 0;
-  while (*s >= '0' && *s <= '9') v = v * 10 + (*s++ - '0');
+  int v = 0, nd = 0;
+  while (*s >= '0' && *s <= '9') {
+    if (++nd > 6) return false;   // no layer index has more digits; keeps the arithmetic far from overflow
+    v = v * 10 + (*s++ - '0');
+  }
   *out = v;
   return true;
 }
@@ -733,7 +905,7 @@ static int set_act_tensor(bvg_vocoder* v, ActW& a, const char* field, const floa
 
 int vocoder_set_tensor(bvg_vocoder* v, const char* name, const float* data, int64_t numel, int is_device) {
   if (!v || !name || !data || numel <= 0) BVG_FAIL(BVG_EINVAL, "bvg_set_tensor: bad argument");
-  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  BVG_DEVICE(v->cfg.device);
   float* tmp = nullptr;
   const float* d = data;
   if (!is_device) {
@@ -756,8 +928,7 @@ int vocoder_set_tensor(bvg_vocoder* v, const char* name, const float* data, int6
                                    : (set_error("unknown tensor name '%s'", name), BVG_EINVAL);
   } else if (eat(s, "resblocks.")) {
     if (!parse_int(s, &n) || n >= v->nst * v->nk || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
-    else if (eat(s, "convs1.") || (s[5] == '2' && eat(s, "convs2."))) {
-      const bool second = s[-2] == '2';
+    else if (bool second = false; eat(s, "convs1.") || (second = eat(s, "convs2."))) {
       if (!parse_int(s, &l) || l >= v->nd || !eat(s, ".")) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
       else {
         ConvW& c = (second ? v->convs2 : v->convs1)[n * v->nd + l];
@@ -845,7 +1016,7 @@ int vocoder_create(const bvg_config* cfg, bvg_vocoder** out) {
     for (int l = 0; l < cfg->num_dilations; ++l)
       if (cfg->resblock_dilations[j][l] < 1) BVG_FAIL(BVG_EINVAL, "bvg_create: bad dilation");
   }
-  BVG_CUDA(cudaSetDevice(cfg->device));
+  BVG_DEVICE(cfg->device);
   int rc = ensure_device_ok();
   if (rc) return rc;
 
@@ -948,7 +1119,7 @@ int vocoder_forward_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
   if (B < 0 || T0 < 0 || !mel_host || !wav_host) BVG_FAIL(BVG_EINVAL, "bad argument");
   if (wav_dtype != 0 && wav_dtype != 1) BVG_FAIL(BVG_EDTYPE, "wav_dtype must be 0 (fp32) or 1 (int16)");
   if (v->E > 0) BVG_FAIL(BVG_EINVAL, "bvg_vocoder_fwd_host: speaker-conditioned generators go through bvg_vocoder_fwd_cond");
-  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  BVG_DEVICE(v->cfg.device);
   const size_t mel_bytes = (size_t)B * v->cfg.num_mels * T0 * sizeof(float);
   const int64_t nw = (int64_t)B * T0 * v->total_up;
   const size_t wav_bytes = (size_t)nw * (wav_dtype ? 2 : 4);
@@ -990,7 +1161,7 @@ int vocoder_forward_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
 
 extern "C" void bvg_destroy(bvg_vocoder* v) {
   if (!v) return;
-  cudaSetDevice(v->cfg.device);
+  DeviceGuard dg(v->cfg.device);
   cudaDeviceSynchronize();
   auto free_conv = [](ConvW& c) {
     if (c.w) cudaFree(c.w);
@@ -1021,57 +1192,47 @@ extern "C" void bvg_destroy(bvg_vocoder* v) {
   delete v;
 }
 
+// captured graphs bake the kernel sequence, its launch parameters and the arena addresses: every option that changes what a
+// forward enqueues drops them
+static int drop_graphs(bvg_vocoder* v) {
+  if (v->graphs.empty()) return BVG_OK;
+  BVG_DEVICE(v->cfg.device);
+  BVG_CUDA(cudaDeviceSynchronize());
+  for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
+  v->graphs.clear();
+  return BVG_OK;
+}
+
 extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
   if (!v || !key) BVG_FAIL(BVG_EINVAL, "bvg_set_option: null argument");
-  if (!strcmp(key, "graph")) v->opt_graph = value;
-  else if (!strcmp(key, "conv_impl")) v->opt_conv_impl = value;
-  else if (!strcmp(key, "umma_variant")) v->opt_umma_variant = value;
-  else if (!strcmp(key, "split_terms")) v->opt_split_terms = value;
-  else if (!strcmp(key, "fast_sin")) v->opt_fast_sin = value;
-  else if (!strcmp(key, "workspace_mb")) v->opt_ws_cap_mb = value;
-  else if (!strcmp(key, "profile")) v->opt_profile = value;
-  else if (!strcmp(key, "fuse_res") || !strcmp(key, "fuse_res_min_kc")) {
-    BVG_CUDA(cudaSetDevice(v->cfg.device));
-    BVG_CUDA(cudaDeviceSynchronize());
-    for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
-    v->graphs.clear();
-    if (!strcmp(key, "fuse_res")) v->opt_fuse_res = value; else v->fuse_res_min_kc = value;
-  }
-  else if (!strcmp(key, "fuse_unit")) {
-    if (value != v->opt_fuse_unit) {
-      BVG_CUDA(cudaSetDevice(v->cfg.device));
-      BVG_CUDA(cudaDeviceSynchronize());
-      for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
-      v->graphs.clear();
-      v->opt_fuse_unit = value;
+  struct Opt { const char* name; int* field; bool plan; };
+  int ws_mb = (int)v->opt_ws_cap_mb;
+  const Opt opts[] = {
+      {"graph", &v->opt_graph, false},          {"profile", &v->opt_profile, false},
+      {"conv_impl", &v->opt_conv_impl, true},   {"split_terms", &v->opt_split_terms, true},
+      {"fast_sin", &v->opt_fast_sin, true},     {"workspace_mb", &ws_mb, true},
+      {"fuse_res", &v->opt_fuse_res, true},     {"fuse_res_min_kc", &v->fuse_res_min_kc, true},
+      {"fuse_act", &v->opt_fuse_act, true},     {"fuse_unit", &v->opt_fuse_unit, true},
+      {"streams", &v->opt_streams, true},       {"conv_own_sm", &v->opt_own_sm, true},
+  };
+  for (const Opt& o : opts) {
+    if (strcmp(key, o.name)) continue;
+    if (*o.field == value) return BVG_OK;
+    if (o.plan) {
+      const int rc = drop_graphs(v);
+      if (rc) return rc;
     }
+    *o.field = value;
+    v->opt_ws_cap_mb = ws_mb;
+    return BVG_OK;
   }
-  else if (!strcmp(key, "fuse_act")) {
-    if (value != v->opt_fuse_act) {
-      BVG_CUDA(cudaSetDevice(v->cfg.device));
-      BVG_CUDA(cudaDeviceSynchronize());
-      for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
-      v->graphs.clear();
-      v->opt_fuse_act = value;
-    }
-  }
-  else if (!strcmp(key, "streams")) {
-    if (value != v->opt_streams) {   // the workspace layout (and any captured graph) depends on it
-      BVG_CUDA(cudaSetDevice(v->cfg.device));
-      BVG_CUDA(cudaDeviceSynchronize());
-      for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second.first);
-      v->graphs.clear();
-      v->opt_streams = value;
-    }
-  }
-  else BVG_FAIL(BVG_EINVAL, "bvg_set_option: unknown option '%s'", key);
-  return BVG_OK;
+  BVG_FAIL(BVG_EINVAL, "bvg_set_option: unknown option '%s'", key);
 }
 
 // Debug: one line per recorded launch (category, shape, ms, achieved rate) to `path`; does not clear.
 extern "C" int bvg_profile_dump(bvg_vocoder* v, const char* path) {
   if (!v || !path) BVG_FAIL(BVG_EINVAL, "bvg_profile_dump: bad argument");
-  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  BVG_DEVICE(v->cfg.device);
   BVG_CUDA(cudaDeviceSynchronize());
   FILE* f = fopen(path, "w");
   if (!f) BVG_FAIL(BVG_EINVAL, "cannot open %s", path);
@@ -1091,7 +1252,7 @@ extern "C" int bvg_profile_dump(bvg_vocoder* v, const char* path) {
 // category 3 is read (read it last).  Synchronises the device.
 extern "C" int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double* work, int* launches) {
   if (!v || category < 0 || category >= CAT_N || !ms || !work || !launches) BVG_FAIL(BVG_EINVAL, "bvg_profile_read: bad argument");
-  BVG_CUDA(cudaSetDevice(v->cfg.device));
+  BVG_DEVICE(v->cfg.device);
   BVG_CUDA(cudaDeviceSynchronize());
   *ms = 0; *work = 0; *launches = 0;
   for (auto& r : v->prof) {
