@@ -53,6 +53,7 @@ extern "C" {
 /* element types of activations at the ABI */
 #define BVG_F32 0
 #define BVG_BF16 1
+#define BVG_F16 2 /* bvg_act1d_fwd only: the reference kernel dispatches half too (type_shim.h:20-43) */
 
 /* precision modes of the whole-vocoder handle */
 #define BVG_MODE_FP32 0 /* fp32 storage, fp32 SIMT convs, accurate sin: <=1e-5 rel. vs fp32 reference */
@@ -73,7 +74,7 @@ uint64_t bvg_launch_count(void);
 /* ------------------------------------------------------------------------
  * Fused anti-aliased activation: up x2 (12-tap kaiser-sinc, replicate pad 5|5)
  * -> Snake/SnakeBeta -> down x2 (12-tap, replicate pad 5|6), one kernel.
- *   dst, src : [B, C, T] contiguous, time fastest (the reference layout), dtype `dtype`
+ *   dst, src : [B, C, T] contiguous, time fastest (the reference layout), dtype `dtype` (BVG_F32 / BVG_BF16 / BVG_F16; fp32 arithmetic)
  *   alpha_log, beta_log : [C] fp32, LOG scale (the kernel applies exp), device
  *   up_taps, down_taps  : [12] fp32 HOST arrays (Activation1d.upsample.filter / .downsample.lowpass.filter;
  *                         construction-time constants, passed to the kernel as launch parameters)

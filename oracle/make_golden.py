@@ -154,6 +154,25 @@ def gen_generators(mod):
     np.savez_compressed(os.path.join(OUT, "generators.npz"), **out)
 
 
+def gen_headline(mod):
+    """The benchmark's own utterances through the unmodified reference: utterance 3 of BASELINE configs[1] (16 x 861 frames,
+    10 s) and utterance 0 of configs[0] (172 frames, 2 s), full 112 M-parameter generator, seed 1234.  The mel is not
+    stored: synth.make_mel(1, 80, T, first_utterance=u) regenerates it (a checksum guards against RNG drift)."""
+    h = config.default_hparams()
+    sd = synth.make_state_dict(h, seed=1234)
+    m = refshim.build_generator(h, sd)
+    out = {"sd_fingerprint": sd_fingerprint(sd)}
+    for name, T, u in (("u861", 861, 3), ("u172", 172, 0)):
+        mel = synth.make_mel(1, h["num_mels"], T, first_utterance=u)
+        with torch.no_grad():
+            wav = m(mel)
+        out[name + ".wav"] = wav.numpy()
+        out[name + ".utterance"] = np.array([u, T])
+        out[name + ".mel_checksum"] = np.array([float(mel.double().sum()), float(mel.double().abs().sum())])
+        print(name, tuple(mel.shape), "->", tuple(wav.shape), "absmax %.4f" % wav.abs().max())
+    np.savez_compressed(os.path.join(OUT, "headline.npz"), **out)
+
+
 def gen_v1():
     """IndexTTS-v1 speaker-conditioned generator (indextts/BigVGAN/models.py:130-250), UNMODIFIED forward
     `m(latent, mel_ref)` including its randomly initialised ECAPA-TDNN speaker encoder; the embedding the encoder produced
@@ -207,6 +226,8 @@ def main():
         gen_activation(mod)
         gen_ampblock(mod)
         gen_generators(mod)
+    if not only or "headline" in only:
+        gen_headline(mod)
     if not only or "v1" in only:
         gen_v1()
 

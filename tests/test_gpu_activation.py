@@ -136,7 +136,9 @@ def test_act1d_errors_and_empty(ops, act_mod):
     with pytest.raises(RuntimeError):
         ops.act1d(torch.zeros(2, 3, 8), a, a, taps, taps, False)                 # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
-        ops.act1d(torch.zeros(2, 3, 8, device=DEV, dtype=torch.float16), a, a, taps, taps, False)
+        ops.act1d(torch.zeros(2, 3, 8, device=DEV, dtype=torch.float64), a, a, taps, taps, False)   # fp32 / bf16 / fp16 only
+    y16 = ops.act1d(torch.zeros(2, 3, 8, device=DEV, dtype=torch.float16), a, a, taps, taps, False)  # type_shim.h:20-43
+    assert y16.dtype == torch.float16 and float(y16.abs().max()) == 0.0
     with pytest.raises(RuntimeError):
         ops.act1d(torch.zeros(2, 3, 8, device=DEV), a, a, taps[:6], taps, False)
     with pytest.raises(NotImplementedError):

@@ -141,3 +141,62 @@ def test_amp_unit_rejects_wide_units(ops):
         run_unit(ops, x, w1, b1, w2, b2, al, be, 1, form=2)
     y = run_unit(ops, x, w1, b1, w2, b2, al, be, 1, form=0)      # falls back to the four layers
     assert y.shape == x.shape
+
+
+def t_(a):
+    import numpy as np
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("tag", ["c16_k3", "c16_k7", "c8_k11"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ampblock1_dropin_vs_reference_golden(pkg, cfg, golden, tag, precision):
+    """The stand-alone `AMPBlock1` drop-in (same constructor / state-dict as bigvgan.py:31-147) on the GPU against outputs of
+    the unmodified reference block (tests/golden/ampblock1.npz): fp32 mode <= 1e-5, bf16 mode (one kernel per unit) >= 38 dB
+    on these 8-16-channel blocks (little averaging over channels)."""
+    g = golden("ampblock1")
+    C, k = {"c16_k3": (16, 3), "c16_k7": (16, 7), "c8_k11": (8, 11)}[tag]
+    import importlib
+    bv = importlib.import_module("voice-tts_b200.bigvgan")
+    blk = bv.AMPBlock1(cfg.default_hparams(), C, k, (1, 3, 5), activation="snakebeta")
+    blk.remove_weight_norm()
+    sd = {key[len(tag) + 4:]: t_(g[key]) for key in g.files if key.startswith(tag + ".sd.")}
+    blk.load_state_dict(sd)
+    blk = blk.to(DEV).eval()
+    x, ref = t_(g[tag + ".x"]), t_(g[tag + ".y"])
+    with torch.no_grad():
+        y = blk(x.to(DEV), precision=precision).cpu()
+    assert y.shape == ref.shape
+    if precision == "fp32":
+        assert (y - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+    else:
+        snr = O.snr_db(ref - x, y - x)      # the residual branches: x passes through in fp32
+        print(tag, "bf16 branch SNR %.1f dB" % snr)
+        assert snr >= 38.0
+
+
+def test_activation1d_dropin_in_quantizer_construction(pkg):
+    """the other call site of the operator, `Activation1d(activation=SnakeBeta(dim, alpha_logscale=True))`
+    as built in indextts/s2mel/modules/quantize.py:95-97 (and the FAcodec decoder blocks): same construction with this
+    package's classes, forward on the GPU against the oracle, fp32 / bf16 / fp16 inputs."""
+    import importlib
+    act_mod = importlib.import_module("voice-tts_b200.activation1d")
+    dim = 40
+    g = torch.Generator().manual_seed(3)
+    m = act_mod.Activation1d(activation=act_mod.SnakeBeta(dim, alpha_logscale=True)).to(DEV)
+    with torch.no_grad():
+        m.act.alpha.copy_(torch.randn(dim, generator=g) * 0.5)
+        m.act.beta.copy_(torch.randn(dim, generator=g) * 0.5)
+    x = torch.randn(3, dim, 333, generator=g)
+    taps = m.upsample.filter.detach().reshape(-1).cpu().double()
+    ref = O.activation1d(x.double(), m.act.alpha.detach().cpu().double(), m.act.beta.detach().cpu().double(), taps, taps)
+    with torch.no_grad():
+        y = m(x.to(DEV)).cpu().double()
+    assert (y - ref).abs().max() <= 1e-5 * float(ref.abs().max())
+    for dt, tol in ((torch.bfloat16, 2.0 ** -7), (torch.float16, 2.0 ** -10)):
+        xq = x.to(dt)
+        refq = O.activation1d(xq.double(), m.act.alpha.detach().cpu().double(), m.act.beta.detach().cpu().double(), taps, taps)
+        with torch.no_grad():
+            yq = m(xq.to(DEV))
+        assert yq.dtype == dt
+        assert (yq.cpu().double() - refq).abs().max() <= tol * float(refq.abs().max())

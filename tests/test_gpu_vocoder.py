@@ -146,6 +146,56 @@ def test_full_generator_bf16_snr(pkg, golden, full_model_sd):
     assert (wav - ref).abs().max() <= 0.02 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("name", ["u861", "u172"])
+def test_headline_utterances_vs_reference_golden(pkg, synth, golden, full_model_sd, name):
+    """The benchmark's own utterances (utterance 3 of BASELINE configs[1], 861 frames = 10 s; utterance 0 of configs[0],
+    172 frames = 2 s) against the unmodified reference (tests/golden/headline.npz, oracle/make_golden.py headline):
+    fp32 mode <= 1e-5 of max-abs, bf16 mode >= 40 dB (measured 112.4 dB / 2.6e-6 and 41.3 dB)."""
+    h, sd = full_model_sd
+    g = golden("headline")
+    u, T = [int(v) for v in g[name + ".utterance"]]
+    mel = synth.make_mel(1, 80, T, first_utterance=u)
+    chk = g[name + ".mel_checksum"]
+    assert abs(float(mel.double().sum()) - chk[0]) <= 1e-6 * abs(chk[0]), "synthetic mel drifted from the one the golden was made with"
+    ref = t(g[name + ".wav"])
+    for precision in ("fp32", "bf16"):
+        m = make(pkg, h, sd, precision)
+        with torch.no_grad():
+            wav = m(mel.to(DEV)).cpu()
+        err = float((wav - ref).abs().max() / ref.abs().max())
+        snr = O.snr_db(ref, wav)
+        print("%s %s: SNR %.2f dB, max-abs rel %.2e" % (name, precision, snr, err))
+        if precision == "fp32":
+            assert err <= 1e-5
+        else:
+            assert snr >= 40.0 and err <= 0.02
+        del m
+        torch.cuda.empty_cache()
+
+
+def test_headline_batch_bf16_vs_fp32_mode_every_utterance(pkg, synth, golden, full_model_sd):
+    """BASELINE configs[1] at full size (16 x 861 frames): the bf16 mode against this library's fp32 mode (which the golden
+    tests pin to the reference, and which is compared with the reference on utterance 3 here): the MINIMUM per-utterance SNR
+    meets the 40 dB bar (measured 41.30 / 41.34 / 41.38 dB min / median / max)."""
+    h, sd = full_model_sd
+    mel = synth.make_mel(16, 80, 861).to(DEV)
+    m32 = make(pkg, h, sd, "fp32")
+    with torch.no_grad():
+        ref = m32(mel).cpu()
+    del m32
+    torch.cuda.empty_cache()
+    m16 = make(pkg, h, sd, "bf16")
+    with torch.no_grad():
+        wav = m16(mel).cpu()
+    g = golden("headline")
+    gold = t(g["u861.wav"])
+    assert (ref[3:4] - gold).abs().max() <= 1e-5 * float(gold.abs().max())
+    per = [O.snr_db(ref[i], wav[i]) for i in range(16)]
+    print("16 x 861: per-utterance SNR min %.2f max %.2f dB" % (min(per), max(per)))
+    assert min(per) >= 40.0
+    assert O.snr_db(gold, wav[3:4]) >= 40.0
+
+
 def test_full_generator_baseline_shape_properties(pkg, synth, full_model_sd):
     """BASELINE config 2 shape (batch 16 x 10 s): the CPU oracle needs ~3 min per
     utterance, so check (a) one utterance of the batch against the same
@@ -186,7 +236,7 @@ def test_forward_host_int16(pkg, synth, cfg):
     wf = m.forward_host(mel, int16=False)
     assert torch.equal(wf, wav)
     expect = torch.clamp(32767 * wav, -32767.0, 32767.0).to(torch.int16)
-    assert (w16.int() - expect.int()).abs().max() <= 1
+    assert torch.equal(w16, expect)      # the kernel truncates exactly as `.type(torch.int16)` does (infer_v2.py:740)
 
 
 def test_no_cpu_fallback(pkg, synth, cfg):
@@ -198,7 +248,12 @@ def test_no_cpu_fallback(pkg, synth, cfg):
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, h["num_mels"] + 1, 4, device=DEV))
     with pytest.raises(RuntimeError):
-        m(torch.zeros(1, h["num_mels"], 4, device=DEV, dtype=torch.float16))
+        m(torch.zeros(1, h["num_mels"], 4, device=DEV, dtype=torch.int32))
+    # half / bfloat16 mels (the v1 pipeline calls its vocoder under fp16 autocast, infer.py:474) are widened, not rejected
+    mel = synth.make_mel(1, h["num_mels"], 9).half()
+    m.load_state_dict(synth.make_state_dict(h, seed=5), strict=False)
+    with torch.no_grad():
+        assert torch.equal(m(mel.to(DEV)), m(mel.float().to(DEV)))
 
 
 OPTION_SETS = [
@@ -294,10 +349,13 @@ def test_full_generator_bf16_vs_fp32_mode_ragged_lengths(pkg, synth, full_model_
     assert wav.shape == (3, 1, T0 * 256) and torch.isfinite(wav).all()
     snr = O.snr_db(ref, wav)
     print("T0=%d: bf16 vs fp32 mode SNR %.2f dB" % (T0, snr))
-    assert snr >= 38.0
-    # the sequence ends are where the edge variants of the kernels run: compare them separately
+    # measured on B200 (tools/snr_probe.py, profiles/r02_snr_probe.txt): 40.65-41.39 dB for T0 >= 2 and 38.94 dB for the
+    # single-frame input, whose 3 x 256 samples lie entirely inside the receptive field of both sequence ends
+    assert snr >= (40.0 if T0 >= 2 else 38.5)
+    # the sequence ends are where the edge variants of the kernels run: compare them separately (measured 40.3-42.0 dB)
     n = min(512, T0 * 256)
-    assert O.snr_db(ref[..., :n], wav[..., :n]) >= 30.0 and O.snr_db(ref[..., -n:], wav[..., -n:]) >= 30.0
+    bar = 39.5 if T0 >= 2 else 38.5
+    assert O.snr_db(ref[..., :n], wav[..., :n]) >= bar and O.snr_db(ref[..., -n:], wav[..., -n:]) >= bar
 
 
 def test_forward_segments_ragged_batching(pkg, synth, full_model_sd):

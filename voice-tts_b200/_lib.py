@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get("BVG_LIB_NAME", "libbvg_b200.so"))   # BVG_LIB_NAME: debug builds only
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 MODE_FP32, MODE_BF16 = 0, 1
 SNAKE, SNAKEBETA = 0, 1
 ACT_FAST_SIN = 1

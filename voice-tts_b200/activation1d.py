@@ -105,5 +105,5 @@ class Activation1d(nn.Module):
     def forward(self, x):
         alpha, beta = self.log_params()
         up, down = self._host_taps()
-        fast = self.fast_sin if self.fast_sin is not None else (x.dtype == torch.bfloat16)
+        fast = self.fast_sin if self.fast_sin is not None else (x.dtype in (torch.bfloat16, torch.float16))
         return ops.act1d(x, alpha, beta, up, down, bool(fast))

@@ -54,9 +54,20 @@ class AMPBlock1(nn.Module):
         self.activations = nn.ModuleList([Activation1d(activation=_make_act(hh, channels)) for _ in range(self.num_layers)])
 
     def forward(self, x, precision="fp32"):
+        """xt = a1(x); xt = c1(xt); xt = a2(xt); xt = c2(xt); x = xt + x per dilation (bigvgan.py:132-141): one
+        `bvg_amp_unit_fwd` call per unit - ONE kernel in bf16 mode for <= 96 channels, the four layers otherwise."""
         acts1, acts2 = self.activations[::2], self.activations[1::2]
+        empty = x.new_empty(0)
         for c1, c2, a1, a2, d in zip(self.convs1, self.convs2, acts1, acts2, self.dilation):
-            xt = a1(x)
+            t1, t2 = a1._host_taps(), a2._host_taps()
+            if t1 == t2 and a1.fast_sin is None and a2.fast_sin is None:
+                al1, be1 = a1.log_params()
+                al2, be2 = a2.log_params()
+                x = ops.amp_unit(x, _folded_weight(c1), c1.bias if c1.bias is not None else empty, _folded_weight(c2),
+                                 c2.bias if c2.bias is not None else empty, al1, be1, al2, be2, t1[0], t1[1], empty, 1.0, False,
+                                 d, precision, 0)
+                continue
+            xt = a1(x)      # units whose two activations carry different filters: layer by layer through the single-layer ops
             xt = ops.conv1d(xt, _folded_weight(c1), c1.bias, d, precision, 0)
             xt = a2(xt)
             xt = ops.conv1d(xt, _folded_weight(c2), c2.bias, 1, precision, 0)
@@ -179,11 +190,16 @@ class BigVGAN(nn.Module):
         cfg.mode = _lib.MODE_BF16 if self.precision == "bf16" else _lib.MODE_FP32
         cfg.device = device.index if device.index is not None else torch.cuda.current_device()
         handle = ctypes.c_void_p()
-        _lib.check(lib.bvg_create(ctypes.byref(cfg), ctypes.byref(handle)), "bvg_create")
+        with torch.cuda.device(device):
+            _lib.check(lib.bvg_create(ctypes.byref(cfg), ctypes.byref(handle)), "bvg_create")
         try:
-            with torch.no_grad():
-                for name, t in self.folded_state_dict().items():
-                    t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            with torch.no_grad(), torch.cuda.device(device):
+                # the folded / converted tensors are produced on torch's current stream; bvg_set_tensor packs them on the
+                # legacy default stream, which does not wait for a non-blocking side stream: order the two explicitly
+                tensors = [(name, t.detach().to(device=device, dtype=torch.float32).contiguous())
+                           for name, t in self.folded_state_dict().items()]
+                torch.cuda.current_stream(device).synchronize()
+                for name, t in tensors:
                     _lib.check(lib.bvg_set_tensor(handle, name.encode(), t.data_ptr(), t.numel(), 1),
                                "bvg_set_tensor(%s)" % name)
             _lib.check(lib.bvg_finalize(handle), "bvg_finalize")
@@ -204,10 +220,14 @@ class BigVGAN(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("BigVGAN (B200 build) runs on CUDA only; got a %s tensor" % x.device)
+        if not x.is_floating_point():
+            raise RuntimeError("BigVGAN expects a floating-point mel, got %s" % x.dtype)
         if self._hid is None or ops._HANDLES[self._hid][3] != x.device.index:
             self._invalidate()
             self._build_native(x.device)
-        return ops.vocoder(x.contiguous(), self._hid)
+        # infer_v2.py:735 passes `vc_target.float()`; the v1 pipeline calls its vocoder under fp16 autocast (infer.py:474):
+        # half / bfloat16 mels are accepted and widened, the generator's arithmetic is set by `precision`
+        return ops.vocoder(x.float().contiguous(), self._hid)
 
     def forward_host(self, mel_cpu, int16=False, out=None):
         """host mel -> host wav through `bvg_vocoder_fwd_host` (H2D + generator + D2H in one
@@ -219,11 +239,17 @@ class BigVGAN(nn.Module):
             raise RuntimeError("move the model to a CUDA device first")
         if self._hid is None:
             self._build_native(dev)
+        if mel_cpu.dim() != 3 or mel_cpu.shape[1] != in_channels(self.h):
+            raise RuntimeError("forward_host expects mel [B, %d, T], got %s" % (in_channels(self.h), tuple(mel_cpu.shape)))
         mel_cpu = mel_cpu.contiguous()
         B, _, T = mel_cpu.shape
         n = T * total_upsample(self.h)
+        want = torch.int16 if int16 else torch.float32
         if out is None:
-            out = torch.empty(B, 1, n, dtype=torch.int16 if int16 else torch.float32)
+            out = torch.empty(B, 1, n, dtype=want)
+        elif out.is_cuda or out.dtype != want or not out.is_contiguous() or out.numel() != B * n:
+            # the native call writes B*T*hop elements of `want` straight into this buffer
+            raise RuntimeError("forward_host: `out` must be a contiguous CPU %s tensor with %d elements" % (want, B * n))
         with torch.cuda.device(dev):
             rc = _lib.load().bvg_vocoder_fwd_host(ops._HANDLES[self._hid][0], mel_cpu.data_ptr(), out.data_ptr(),
                                                   1 if int16 else 0, B, T, torch.cuda.current_stream(dev).cuda_stream)

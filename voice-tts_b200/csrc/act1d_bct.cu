@@ -247,6 +247,9 @@ int act1d_bct_launch(void* dst, const void* src, const float* alpha_log, const f
   if (dtype == BVG_BF16)
     return fast ? launch_bct<__nv_bfloat16, true>(dst, src, alpha_log, beta_log, taps, B, C, T, st)
                 : launch_bct<__nv_bfloat16, false>(dst, src, alpha_log, beta_log, taps, B, C, T, st);
+  if (dtype == BVG_F16)   // the reference kernel dispatches half as well (type_shim.h:20-43); the arithmetic is fp32 as for bf16
+    return fast ? launch_bct<__half, true>(dst, src, alpha_log, beta_log, taps, B, C, T, st)
+                : launch_bct<__half, false>(dst, src, alpha_log, beta_log, taps, B, C, T, st);
   BVG_FAIL(BVG_EDTYPE, "act1d: unsupported dtype %d", dtype);
 }
 

@@ -75,11 +75,11 @@ uint64_t bvg_launch_count(void) { return g_launches.load(); }
 int bvg_act1d_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log, const float* up_taps,
                   const float* down_taps, int B, int C, int64_t T, int dtype, int flags, bvg_stream_t stream) {
   if (B < 0 || C < 0 || T < 0) BVG_FAIL(BVG_EINVAL, "bvg_act1d_fwd: negative dimension");
-  if (dtype != BVG_F32 && dtype != BVG_BF16) BVG_FAIL(BVG_EDTYPE, "bvg_act1d_fwd: unsupported dtype %d", dtype);
+  if (dtype != BVG_F32 && dtype != BVG_BF16 && dtype != BVG_F16) BVG_FAIL(BVG_EDTYPE, "bvg_act1d_fwd: unsupported dtype %d", dtype);
   if (B == 0 || C == 0 || T == 0) return BVG_OK;  // reference: seq_len == 0 -> no launch
   if (!dst || !src || !alpha_log || !beta_log || !up_taps || !down_taps) BVG_FAIL(BVG_EINVAL, "bvg_act1d_fwd: null pointer");
   if (dst == src) BVG_FAIL(BVG_EINVAL, "bvg_act1d_fwd: dst must not alias src");
-  const size_t es = dtype == BVG_BF16 ? 2 : 4;
+  const size_t es = dtype == BVG_F32 ? 4 : 2;
   if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % es)
     BVG_FAIL(BVG_EALIGN, "bvg_act1d_fwd: dst/src must be aligned to the element size");
   int rc = ensure_device_ok();

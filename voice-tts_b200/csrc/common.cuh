@@ -1,6 +1,7 @@
 // Shared host/device helpers for libbvg_b200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -101,6 +102,8 @@ template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 
 // one element of a tensor another kernel may rewrite (see BVG_LDG), as fp32
 template <typename T>
@@ -118,6 +121,8 @@ template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
 // sin(x) up to sign: sin(x - k*pi) with k = rint(x / pi).  The snake only uses sin^2, so the (-1)^k is never
 // needed.  3-term Cody-Waite reduction (the products k*PI_HI, k*PI_MID are exact for |x| < ~1e4) and a degree-9

@@ -479,7 +479,8 @@ int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   const int smem = a.own_sm ? U2_SMEM_BYTES : U2_SMEM_USED;
 #define BVG_U2_LAUNCH(N, O)                                                                                          \
   do {                                                                                                               \
-    BVG_CUDA(cudaFuncSetAttribute(conv_umma2_kernel<N, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES)); \
+    static std::atomic<unsigned long long> attr_done_{0};                                                              \
+    if (int rc_ = smem_attr_once(conv_umma2_kernel<N, O>, U2_SMEM_BYTES, attr_done_)) return rc_;                      \
     conv_umma2_kernel<N, O><<<grid, U2_THREADS, smem, st>>>(mx, mw, mo, mr, ma, p);                         \
   } while (0)
   const bool ob = a.out_dtype == BVG_BF16;

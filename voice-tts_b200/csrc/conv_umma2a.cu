@@ -571,10 +571,12 @@ int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* b
   const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
   const int smem = a.own_sm ? UA_SMEM_BYTES : UA_SMEM_USED;
   if (a.res) {
-    BVG_CUDA(cudaFuncSetAttribute(conv_umma2a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES));
+    static std::atomic<unsigned long long> attr_done_res{0};
+    if (int rc_ = smem_attr_once(conv_umma2a_kernel<true>, UA_SMEM_BYTES, attr_done_res)) return rc_;
     conv_umma2a_kernel<true><<<grid, UA_THREADS, smem, st>>>(mx, mw, mo, mt, p);
   } else {
-    BVG_CUDA(cudaFuncSetAttribute(conv_umma2a_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES));
+    static std::atomic<unsigned long long> attr_done_plain{0};
+    if (int rc_ = smem_attr_once(conv_umma2a_kernel<false>, UA_SMEM_BYTES, attr_done_plain)) return rc_;
     conv_umma2a_kernel<false><<<grid, UA_THREADS, smem, st>>>(mx, mw, mo, mt, p);
   }
   BVG_LAUNCHED();

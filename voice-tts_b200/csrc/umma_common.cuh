@@ -27,6 +27,18 @@ int make_map_4d_w(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, ui
 int make_map_any(CUtensorMap* m, const void* base, int es, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
                  uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
 int umma_sm_count();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device and kernel instantiation instead of once per launch
+// (`done`: one bit per device ordinal; the attribute is per device)
+template <typename K>
+static inline int smem_attr_once(K kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  BVG_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return BVG_OK;
+  BVG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  return BVG_OK;
+}
 // v2 channel-major kernel (conv_umma2.cu): 128-byte operand rows, TMA-store epilogue
 bool conv_umma2_supported(const ConvArgs& a);
 int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st);

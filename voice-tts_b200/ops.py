@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+_DT_ACT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}   # bvg_act1d_fwd also takes half
 
 
 def _stream(t):
@@ -32,8 +33,8 @@ def act1d(x: torch.Tensor, alpha_log: torch.Tensor, beta_log: torch.Tensor, up_t
     if x.dim() != 3:
         raise RuntimeError("act1d expects [B, C, T], got %s" % (tuple(x.shape),))
     _require_cuda(x, "x")
-    if x.dtype not in _DT:
-        raise RuntimeError("act1d supports float32 and bfloat16, got %s" % x.dtype)
+    if x.dtype not in _DT_ACT:
+        raise RuntimeError("act1d supports float32, bfloat16 and float16, got %s" % x.dtype)
     B, C, T = x.shape
     a = alpha_log.detach().to(device=x.device, dtype=torch.float32).contiguous()
     b = beta_log.detach().to(device=x.device, dtype=torch.float32).contiguous()
@@ -43,7 +44,7 @@ def act1d(x: torch.Tensor, alpha_log: torch.Tensor, beta_log: torch.Tensor, up_t
     lib = _lib.load()
     with torch.cuda.device(x.device):
         rc = lib.bvg_act1d_fwd(y.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), _lib.taps_array(up_taps),
-                               _lib.taps_array(down_taps), B, C, T, _DT[x.dtype],
+                               _lib.taps_array(down_taps), B, C, T, _DT_ACT[x.dtype],
                                _lib.ACT_FAST_SIN if fast else 0, _stream(x))
     _lib.check(rc, "bvg_act1d_fwd")
     return y
