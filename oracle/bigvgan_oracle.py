@@ -191,12 +191,31 @@ def fold_weight_norm(sd):
 # --------------------------------------------------------------------------
 # blocks and generator
 # --------------------------------------------------------------------------
+_STAGED = False   # see `staged_ops`
+
+
+class staged_ops:
+    """Context manager: inside it every Activation1d of the generator runs as `activation1d_staged`, i.e. the reference's
+    own operator sequence (F.pad replicate -> conv_transpose1d -> slice -> snake -> F.pad -> strided conv1d, resample.py:29-38,
+    filter.py:94-101) instead of the closed polyphase form.  The two agree to rounding (tests/test_oracle.py); the staged form
+    is what `bench.py` times as the CPU arm, because it costs what the reference costs on the host (measured in the build
+    container against the imported reference)."""
+
+    def __enter__(self):
+        global _STAGED
+        self.prev, _STAGED = _STAGED, True
+
+    def __exit__(self, *exc):
+        global _STAGED
+        _STAGED = self.prev
+
+
 def _act(sd, prefix, x, h):
     logscale = h.get("snake_logscale", True)
     alpha = sd[prefix + ".act.alpha"]
     beta = sd[prefix + ".act.beta"] if h["activation"] == "snakebeta" else alpha
-    return activation1d(x, alpha, beta, sd[prefix + ".upsample.filter"],
-                        sd[prefix + ".downsample.lowpass.filter"], logscale)
+    fn = activation1d_staged if _STAGED else activation1d
+    return fn(x, alpha, beta, sd[prefix + ".upsample.filter"], sd[prefix + ".downsample.lowpass.filter"], logscale)
 
 
 def amp_block1(sd, prefix, x, h, dilations):
