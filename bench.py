@@ -12,9 +12,15 @@ wall-second over all ranks with the mels already resident in HBM; `e2e` = the
 same through the host-buffer C-ABI call (`bvg_vocoder_fwd_host`: pinned H2D of
 the mels + generator + D2H of the waveform inside the timed region).
 
-`--impl reference` times the reference algorithm on the host cores (the oracle
-port of the reference's torch path - the Python reference itself cannot travel
-to the GPU box) on a bounded sample of the same workload.
+`--impl reference` times the reference's CPU path on the host cores: the oracle's
+staged form, i.e. the reference's own operator sequence (F.pad / conv_transpose1d /
+conv1d / snake), bit-identical to the imported reference and within 5 % of its wall
+time in the build container (tools/cpu_arm_check.py; the Python reference itself
+cannot travel to the GPU box) - on a bounded sample of the same workload: ONE
+utterance of the workload's shape per step.
+
+`--workload c4` is BASELINE configs[3]: a global batch of 256 utterances x 30 s sharded
+256/N over the ranks (strong scaling), micro-batched inside `bvg_vocoder_fwd`.
 """
 import argparse
 import contextlib
@@ -45,12 +51,37 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step")
-    ap.add_argument("--frames", type=int, default=861, help="mel frames per utterance (861 = 10 s)")
+    ap.add_argument("--workload", default="headline", choices=["headline", "c4"],
+                    help="headline: BASELINE configs[1], 16 x 10 s per GPU (weak scaling); c4: configs[3], 256 x 30 s global (strong)")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU per step (headline) / in total (c4)")
+    ap.add_argument("--frames", type=int, default=None, help="mel frames per utterance (861 = 10 s, 2584 = 30 s)")
+    ap.add_argument("--repeats", type=int, default=3, help="the K-step timed region is repeated this often; value = median")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--act-sweep", action="store_true", help="also print the fused-activation HBM sweep (config 3)")
-    return ap.parse_args()
+    ap.add_argument("--act-sweep", action="store_true", help="include the full fused-activation HBM sweep table (config 3)")
+    ap.add_argument("--no-act-sweep", action="store_true", help="skip the activation sweep summary")
+    ap.add_argument("--no-extras", action="store_true", help="headline numbers only (no precision modes, sweep, latency table)")
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 256 if a.workload == "c4" else 16
+    if a.frames is None:
+        a.frames = 2584 if a.workload == "c4" else 861
+    return a
+
+
+def workload_config(args, world):
+    """`config` of the JSON line - identical in both arms (the reference arm times a bounded sample of it)."""
+    if args.workload == "c4":
+        return {"workload": "bigvgan_v2_22khz_80band_256x generator, global batch of %d utterances x %d mel frames (%.1f s) sharded "
+                            "%d/N over the ranks per step (BASELINE configs[3])" % (args.batch, args.frames, args.frames * HOP / SR, args.batch),
+                "global_batch": args.batch, "parallelism": "batch-sharded x%d, no collective" % world,
+                "weights": "random-init (seed 1234), alpha/beta ~ N(0,0.5)",
+                "l2": "no explicit flush: each step streams a multi-GB workspace + 0.22 GB weights (>> 126 MB L2)"}
+    return {"workload": "bigvgan_v2_22khz_80band_256x generator, %d utterances x %d mel frames (%.1f s) per GPU per step"
+                        % (args.batch, args.frames, args.frames * HOP / SR),
+            "global_batch": args.batch * world, "parallelism": "batch-sharded x%d, no collective" % world,
+            "weights": "random-init (seed 1234), alpha/beta ~ N(0,0.5)",
+            "l2": "no explicit flush: each step streams a multi-GB workspace + 0.22 GB weights (>> 126 MB L2)"}
 
 
 def peaks():
@@ -115,19 +146,26 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_forward_rate(h, sd, frames, runs, threads):
-    """audio-s per wall-s of the oracle port (reference torch algorithm) on the host cores."""
-    import torch
+def cpu_forward(h, sd, mel):
+    """one forward of the reference's CPU path: the oracle in its staged form = the reference's own operator sequence
+    (bit-identical to the imported reference, 1.05x its wall time: tools/cpu_arm_check.py)"""
     from oracle import bigvgan_oracle as O
+    with O.staged_ops():
+        return O.generator_forward(sd, h, mel)
+
+
+def cpu_forward_rate(h, sd, frames, runs, threads):
+    """audio-s per wall-s of the reference's CPU path on the host cores (median of `runs` after one warm-up)."""
+    import torch
     synth = importlib.import_module("voice-tts_b200.synth")
     torch.set_num_threads(threads)
     mel = synth.make_mel(1, h["num_mels"], frames)
     with torch.no_grad():
-        O.generator_forward(sd, h, mel)  # warm-up
+        cpu_forward(h, sd, mel)  # warm-up
         ts = []
         for _ in range(runs):
             t0 = time.perf_counter()
-            O.generator_forward(sd, h, mel)
+            cpu_forward(h, sd, mel)
             ts.append(time.perf_counter() - t0)
     ts.sort()
     med = ts[len(ts) // 2]
@@ -146,41 +184,49 @@ def cpu_model_name():
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU implementation of the path (oracle port), all host threads."""
+    """Reference arm: the reference's CPU implementation of the path on all host threads.  Each step is a bounded sample of
+    the workload: ONE utterance of the workload's shape (fewer frames only if the host is too slow for the time budget)."""
     if rank != 0:
         return
     import torch
     cfg = importlib.import_module("voice-tts_b200.config")
     synth = importlib.import_module("voice-tts_b200.synth")
-    from oracle import bigvgan_oracle as O
     h = cfg.default_hparams()
     sd = synth.make_state_dict(h, seed=1234)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    # size the per-step sample so that the whole run stays within ~2.5 minutes
+    # one utterance of the workload's own shape per step, unless a probe says the whole run would exceed ~4 minutes
     probe_frames = 43
     rate, t_probe = cpu_forward_rate(h, sd, probe_frames, 1, threads)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    frames = int(max(22, min(args.frames, probe_frames * budget / t_probe)))
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    frames = int(max(22, min(args.frames, probe_frames * budget / (2.0 * t_probe))))   # x2: long utterances run ~2x slower per frame (caches)
     mel = synth.make_mel(1, h["num_mels"], frames)
+    ts = []
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.generator_forward(sd, h, mel)
+            cpu_forward(h, sd, mel)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.generator_forward(sd, h, mel)
+            t1 = time.perf_counter()
+            cpu_forward(h, sd, mel)
+            ts.append(time.perf_counter() - t1)
         dt = time.perf_counter() - t0
     audio_s = frames * HOP / SR
     value = audio_s * args.steps / dt
-    sample = "1 utterance x %d mel frames (%.2f s audio) per step, fp32, torch %s CPU, %s" % (
-        frames, audio_s, torch.__version__, cpu_model_name())
+    ts.sort()
+    sample = "1 utterance x %d mel frames (%.2f s audio) per step%s, fp32, reference operator sequence (oracle staged form), torch %s CPU, %s" % (
+        frames, audio_s, "" if frames == args.frames else " (the workload's %d frames cut to the time budget)" % args.frames,
+        torch.__version__, cpu_model_name())
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bigvgan_v2_22khz_80band_256x, batch %d x %d frames per GPU (CPU arm: bounded sample)"
-                               % (args.batch, args.frames), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "median_step_s": ts[len(ts) // 2],
+                         "kind_note": "the reference's own operator sequence on torch CPU (bit-identical outputs, 1.05x the wall time of "
+                                      "the imported reference in the build container); the Python reference cannot travel to the GPU box"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -278,6 +324,28 @@ def top_launch_stats(model, pk):
         return {"error": str(exc)}
 
 
+def act_sweep_summary(rows, pk):
+    """min / median / max fraction of the measured HBM copy rate per series, and the large-T points (T >= 131072)."""
+    out = {}
+    for r in rows:
+        key = "%s %s %s" % (r["impl"], r["dtype"], r["snake"])
+        out.setdefault(key, []).append(r)
+    summ = {}
+    for key, rs in out.items():
+        fr = sorted(x["frac_hbm"] for x in rs)
+        big = sorted(x["frac_hbm"] for x in rs if x["T"] >= 131072)
+        summ[key] = {"points": len(fr), "frac_min": fr[0], "frac_median": fr[len(fr) // 2], "frac_max": fr[-1],
+                     "frac_median_T_ge_131072": big[len(big) // 2] if big else None,
+                     "GBps_max": max(x["GBps"] for x in rs)}
+    return {"peak_GBps": pk["hbm_gbs"], "layout": "[B,C,T] operator layout (bvg_act1d_fwd), >= 256 MB tensors, L2 flushed between runs, "
+            "C in 24..1536, T in 8K..2M, algorithmic bytes = 2*B*C*T*sizeof(dtype)", "series": summ}
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -301,6 +369,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
+    c4 = args.workload == "c4"
+    extras = not args.no_extras and not c4
 
     h = cfg.default_hparams()
     sd = synth.make_state_dict(h, seed=1234)
@@ -310,11 +380,18 @@ def main():
     model.load_state_dict(sd)
     model = model.to(dev).eval()
 
-    B, T0 = args.batch, args.frames
-    audio_s_step = B * T0 * HOP / SR
-    # utterances are sharded by rank (weak scaling: B per GPU): rank r vocodes [r*B, (r+1)*B) of the global batch
-    lo, hi = shard.shard_range(B * world, rank, world)
-    mel_host = synth.make_mel(hi - lo, h["num_mels"], T0, first_utterance=lo).pin_memory()
+    T0 = args.frames
+    if c4:
+        # strong scaling: the global batch is fixed, rank r vocodes utterances shard_range(B_global, r, world)
+        B_global = args.batch
+        lo, hi = shard.shard_range(B_global, rank, world)
+    else:
+        # weak scaling: B utterances per GPU, rank r vocodes [r*B, (r+1)*B) of the global batch
+        B_global = args.batch * world
+        lo, hi = shard.shard_range(B_global, rank, world)
+    B = hi - lo
+    audio_s_step = B_global * T0 * HOP / SR          # audio-seconds ALL ranks produce per step
+    mel_host = synth.make_mel(B, h["num_mels"], T0, first_utterance=lo).pin_memory()
     mel = mel_host.to(dev, non_blocking=True)
     wav_host = torch.empty(B, 1, T0 * cfg.total_upsample(h), dtype=torch.float32).pin_memory()
 
@@ -342,17 +419,41 @@ def main():
             barrier()
             return max_over_ranks(e0.elapsed_time(e1)), w
 
-        # ---- device-resident throughput: K steps, CUDA events around the region, max over ranks ----
+        def timed_e2e():
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                model.forward_host(mel_host, out=wav_host)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            return dt
+
+        for _ in range(2):
+            model.forward_host(mel_host, out=wav_host)
+        # ---- `repeats` x (K device-resident steps, K end-to-end steps), interleaved so that both see the same clocks;
+        #      value / e2e = the median region.  Device-resident: CUDA events around the K steps, max over ranks.
+        #      End to end: BigVGAN.forward_host -> bvg_vocoder_fwd_host (pinned H2D of the mels + generator + D2H of the
+        #      waveform inside the timed region), wall clock, max over ranks. ----
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        n0 = _lib.launch_count()
-        ms, wav = timed_steps()
-        launches = _lib.launch_count() - n0
+        ms_runs, e2e_runs, launches = [], [], 0
+        for r in range(max(1, args.repeats)):
+            n0 = _lib.launch_count()
+            ms_r, wav = timed_steps()
+            if r == 0:
+                launches = _lib.launch_count() - n0
+            ms_runs.append(ms_r)
+            e2e_runs.append(timed_e2e())
+        ms = median(ms_runs)
+        e2e_s = median(e2e_runs)
+        clocks = sampler.stop() if rank == 0 else None
+
         # ---- the same K steps again, serial schedule (streams = 1), with one CUDA-event pair per kernel on the launch
         #      stream (roofline / time split).  An event between two launches keeps the next kernel from being issued
         #      while the previous one drains (~5-9 us per launch, 2-4 % of the step), and per-kernel times only add up
-        #      when kernels do not overlap, so the headline comes from the un-instrumented default pass above and this
+        #      when kernels do not overlap, so the headline comes from the un-instrumented default passes above and this
         #      pass reports its own ms_per_step beside the per-kernel sums. ----
         wav_default = wav.clone()
         model.set_option("streams", 1)
@@ -364,7 +465,6 @@ def main():
         model(mel)
         model.read_profile()
         ms_prof, _ = timed_steps()
-        clocks = sampler.stop() if rank == 0 else None
         top_launch = None
         if rank == 0:
             top_launch = top_launch_stats(model, pk)
@@ -373,33 +473,29 @@ def main():
         model.set_option("streams", 3)
         del wav_default, wav_s
 
-        # ---- latency of ONE utterance (BASELINE configs[0] shape: 172 frames = 2 s), the way infer_v2 calls the vocoder ----
-        mel1 = mel[:1, :, :172].contiguous()
-        for _ in range(5):
-            model(mel1)
-        barrier()
-        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e4.record()
-        for _ in range(50):
-            model(mel1)
-        e5.record()
-        barrier()
-        ms_one = max_over_ranks(e4.elapsed_time(e5)) / 50
+        # ---- latency of ONE utterance, the way infer_v2 calls the vocoder (batch 1, one segment): 2 s (BASELINE
+        #      configs[0] shape) and 10 s, repeated shapes (CUDA-graph replay after the first call of a shape) ----
+        latency = {}
+        if not c4:
+            for frames in (172, 861):
+                mel1 = mel[:1, :, :frames].contiguous() if T0 >= frames else None
+                if mel1 is None:
+                    continue
+                for _ in range(5):
+                    model(mel1)
+                barrier()
+                e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e4.record()
+                for _ in range(50):
+                    model(mel1)
+                e5.record()
+                barrier()
+                ms_one = max_over_ranks(e4.elapsed_time(e5)) / 50
+                latency[frames] = {"frames": frames, "audio_s": frames * HOP / SR, "ms": ms_one,
+                                   "x_realtime": frames * HOP / SR / (ms_one * 1e-3)}
 
-        # ---- end to end through the host-buffer C ABI call ----
-        model.set_option("profile", 0)
-        for _ in range(2):
-            model.forward_host(mel_host, out=wav_host)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            model.forward_host(mel_host, out=wav_host)
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-
-    value = world * audio_s_step * args.steps / (ms * 1e-3)
-    e2e_value = world * audio_s_step * args.steps / e2e_s
+    value = audio_s_step * args.steps / (ms * 1e-3)
+    e2e_value = audio_s_step * args.steps / e2e_s
 
     # ---- roofline of the dominant kernel (live CUDA-event durations of this run) ----
     c_ms, c_flops, c_n = prof["conv_tcgen05"]
@@ -416,21 +512,24 @@ def main():
     tensor_peak = pk["bf16_tflops_sustained"]
     ach_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     ach_gb = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
-    # DRAM traffic per launch from the committed ncu capture of one forward of the SAME workload (tools/ncu_traffic.py ->
-    # profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the kernel's launches / launches)
-    traffic = {}
-    try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
-        if B == 16 and T0 == 861 and args.precision == "bf16":
-            traffic = tj
-    except Exception:
-        pass
+    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of every launch of ONE forward of the SAME workload
+    # from the committed ncu capture (tools/ncu_traffic.py -> profiles/r02_traffic.json; ncu cannot run inside a timed bench)
+    traffic, traffic_file = {}, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if args.batch == 16 and T0 == 861 and args.precision == "bf16" and not c4:
+                traffic, traffic_file = tj, name
+            break
+        except Exception:
+            continue
     roofline = {"kernel": conv_name, "bound": "tensor", "achieved": round(ach_tf, 2), "peak": tensor_peak,
                 "unit": "TFLOP/s", "frac": round(ach_tf / tensor_peak, 4),
+                "frac_of_burst_peak": round(ach_tf / pk["bf16_tflops"], 4),
                 "traffic": traffic.get("conv_tcgen05", {}).get("dram_bytes_per_launch") if c_n else None,
-                "traffic_note": "bytes per launch averaged over the 115 conv launches of one forward (profiles/r01_traffic.txt); operands + results of the padded tensors, no re-reads",
+                "traffic_note": "bytes per launch averaged over the conv launches of one forward (ncu capture of the same workload, profiles/%s); operands + results of the padded tensors, no re-reads" % traffic_file,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
-                "measured": "one CUDA-event pair per launch on the launch stream, summed over a second pass of the same K steps",
+                "measured": "one CUDA-event pair per launch on the launch stream, summed over a separate pass of the same K steps",
                 "share_of_step": round(conv_ms / tot, 3) if tot else None, "launches": conv_n,
                 "avg_launch_ms": round(conv_ms / max(conv_n, 1), 4)}
     if top_launch:
@@ -442,16 +541,14 @@ def main():
                     "algorithmic_bytes_per_launch": round(a_bytes / max(a_n, 1), 1),
                     "share_of_step": round(a_ms / tot, 3) if tot else None, "launches": a_n}
 
+    config = workload_config(args, world)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if c4 else "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "bigvgan_v2_22khz_80band_256x generator, %d utterances x %d mel frames (%.1f s) per GPU per step"
-                               % (B, T0, T0 * HOP / SR),
-                   "global_batch": B * world, "parallelism": "batch-sharded x%d, no collective" % world,
-                   "weights": "random-init (seed 1234), alpha/beta ~ N(0,0.5)",
-                   "l2": "no explicit flush: each step streams a %.1f GB workspace + 0.22 GB weights (>> 126 MB L2)"
-                         % (model_workspace_gb(model, B, T0))},
+        "config": config,
+        "repeats": {"n": len(ms_runs), "statistic": "median", "ms_per_step": [round(x / args.steps, 4) for x in ms_runs],
+                    "e2e_ms_per_step": [round(1e3 * x / args.steps, 4) for x in e2e_runs]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4,
                 "d2h_bytes_per_step": wav_host.numel() * 4, "api": "BigVGAN.forward_host -> bvg_vocoder_fwd_host"},
         "gpu_launches": int(launches),
@@ -462,22 +559,30 @@ def main():
                                    "activation": a_ms / args.steps, "other": o_ms / args.steps,
                                    "of_which_amp_unit_kernels": u_ms / args.steps},
         "x_realtime_per_gpu": value / world,
+        "utterances_per_rank": B,
+        "workspace_gb_per_gpu": round(model_workspace_gb(model, B, T0), 2),
         "profile_pass_ms_per_step": ms_prof / args.steps,
-        "serial_schedule": {"value": world * audio_s_step * args.steps / (ms_serial * 1e-3), "unit": UNIT,
+        "serial_schedule": {"value": audio_s_step * args.steps / (ms_serial * 1e-3), "unit": UNIT,
                             "ms_per_step": ms_serial / args.steps, "bit_identical_to_default": serial_identical,
                             "note": "bvg_set_option('streams', 1); the default runs the 3 AMP blocks of a stage on 3 streams"},
-        "single_utterance": {"frames": 172, "audio_s": 172 * HOP / SR, "ms": ms_one,
-                             "x_realtime": 172 * HOP / SR / (ms_one * 1e-3)},
     }
+    if 172 in latency:
+        out["single_utterance"] = latency[172]
+    if 861 in latency:
+        out["single_utterance_10s"] = latency[861]
 
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         threads = os.cpu_count() or 1
-        # bounded sample: one 2 s utterance (BASELINE configs[0]) - ~10-30 s of CPU work
-        rate, med = cpu_forward_rate(h, sd, 172, 3, threads)
+        # bounded sample: ONE utterance of the workload's own shape (10 s: ~10-30 s of CPU work for 1 warm-up + 3 runs);
+        # a probe shortens it on a slow host
+        rate_p, t_p = cpu_forward_rate(h, sd, 43, 1, threads)
+        frames = int(max(43, min(T0, 43 * 12.0 / (2.0 * t_p))))    # <= ~12 s per forward (long utterances cost ~2x per frame)
+        rate, med = cpu_forward_rate(h, sd, frames, 3, threads)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": "oracle port of the reference torch path, fp32, 1 utterance x 172 frames (2.0 s), "
-                                         "median of 3 after 1 warm-up, %.2f s per forward, %s" % (med, cpu_model_name())}
-    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_cpu_baseline:
+                               "sample": "reference operator sequence on torch CPU (oracle staged form: bit-identical to the imported "
+                                         "reference, 1.05x its wall time in the build container), fp32, 1 utterance x %d frames (%.1f s), "
+                                         "median of 3 after 1 warm-up, %.2f s per forward, %s" % (frames, frames * HOP / SR, med, cpu_model_name())}
+    if rank == 0 and world == 1 and args.precision == "bf16" and extras and not args.no_cpu_baseline:
         # the other precision modes on the same workload (reported beside the headline, not part of it): "fp32" is the
         # <= 1e-5 parity mode (SIMT convolutions), "bf16x3" fp32 storage with three bf16 tensor-core passes per convolution
         out["precision_modes"] = {}
@@ -505,8 +610,15 @@ def main():
                 torch.cuda.empty_cache()
             except Exception as e:  # a reported extra must never cost the headline line
                 out["precision_modes"][prec] = {"error": str(e)[:200]}
-    if rank == 0 and args.act_sweep:
-        out["activation_sweep"] = act_sweep(dev, pk)
+    if rank == 0 and world == 1 and extras and not args.no_act_sweep:
+        # BASELINE configs[2]: the fused-activation HBM sweep (summary always, full table with --act-sweep)
+        try:
+            rows = act_sweep(dev, pk)
+            out["activation_sweep_summary"] = act_sweep_summary(rows, pk)
+            if args.act_sweep:
+                out["activation_sweep"] = rows
+        except Exception as e:
+            out["activation_sweep_summary"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
