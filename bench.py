@@ -495,7 +495,11 @@ def main():
                                    "x_realtime": frames * HOP / SR / (ms_one * 1e-3)}
 
     value = audio_s_step * args.steps / (ms * 1e-3)
-    e2e_value = audio_s_step * args.steps / e2e_s
+    e2e_measured = audio_s_step * args.steps / e2e_s
+    # the end-to-end pass does strictly more work per step (the same kernels plus the two PCIe copies); when its median
+    # region nevertheless comes out ahead of the device-resident one (clock drift under the power cap: the regions differ
+    # by ~1 %), the lower figure is reported and the measured one kept beside it
+    e2e_value = min(e2e_measured, value)
 
     # ---- roofline of the dominant kernel (live CUDA-event durations of this run) ----
     c_ms, c_flops, c_n = prof["conv_tcgen05"]
@@ -550,7 +554,8 @@ def main():
         "repeats": {"n": len(ms_runs), "statistic": "median", "ms_per_step": [round(x / args.steps, 4) for x in ms_runs],
                     "e2e_ms_per_step": [round(1e3 * x / args.steps, 4) for x in e2e_runs]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4,
-                "d2h_bytes_per_step": wav_host.numel() * 4, "api": "BigVGAN.forward_host -> bvg_vocoder_fwd_host"},
+                "d2h_bytes_per_step": wav_host.numel() * 4, "api": "BigVGAN.forward_host -> bvg_vocoder_fwd_host",
+                "measured": e2e_measured},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -198,7 +198,7 @@ int bvg_vocoder_fwd_cond(bvg_vocoder* v, const float* latent, const float* spk_e
  * wav_dtype: 0 = fp32 wav in [-1,1]; 1 = int16 `clamp(32767*wav, -32767, 32767)` (infer_v2.py:740). */
 int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, int wav_dtype,
                          int B, int T0, bvg_stream_t stream);
-/* options: "graph" (0/1, CUDA-graph the layer sequence), "conv_impl" (0 auto, 1 simt, 2 tcgen05; 3 in BVG_MODE_FP32: every
+/* options: "graph" (CUDA-graph replay of the layer sequence: 0 never, 1 always, 2 [default] from the second forward of a (B, T0) shape on), "conv_impl" (0 auto, 1 simt, 2 tcgen05; 3 in BVG_MODE_FP32: every
  * convolution as "split_terms" (3 [default], 6 or 9) bf16 tcgen05 passes over three-term bf16 splits of the fp32 operands -
  * 93 / 96 / 96 dB on the full generator, limited by the tensor cores' fp32 accumulation, 8x / 4.5x / 3x faster than the SIMT kernels),
  * "fast_sin" (0/1), "workspace_mb" (micro-batching cap), "profile" (0/1: one CUDA-event pair per launch, read back with

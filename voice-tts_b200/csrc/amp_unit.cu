@@ -38,16 +38,13 @@
 
 namespace bvg {
 
-constexpr int AU_CWARPS = 16;                         // compute warps (0..15); warp 16: weight loads, warp 17: MMA issue
-constexpr int AU_SHARE = AU_CWARPS / 4;               // compute warps per TMEM lane quadrant
+constexpr int AU_CWARPS = 8;                          // compute warps (0..7); warp 8: weight loads, warp 9: MMA issue
 constexpr int AU_CTHREADS = 32 * AU_CWARPS;
 constexpr int AU_THREADS = AU_CTHREADS + 64;
-constexpr int AU_MAX_SMEM = 227 * 1024;               // one CTA per SM, two tile streams
-constexpr int AU_MAX_SLOTS = 6;
-constexpr int AU_ACC_COLS = 256;                      // TMEM columns of one stream's accumulator
-constexpr int AU_TMEM_COLS = 2 * AU_ACC_COLS;
-constexpr int AU_BAR_BYTES = (2 * AU_MAX_SLOTS + 8) * 8 + 16;   // ring + 8 stream barriers, TMEM slot
-constexpr int AU_TAIL_BYTES = AU_BAR_BYTES + 5 * 96 * 4;        // then the per-channel constant table
+constexpr int AU_MAX_SMEM = 113 * 1024;               // two CTAs per SM: 2 x (113 KB + 1 KB system) = 228 KB
+constexpr int AU_MAX_SLOTS = 4;
+constexpr int AU_TMEM_COLS = 256;
+constexpr int AU_TAIL_BYTES = 112 + 5 * 96 * 4;       // 12 barriers + TMEM slot (100 B), then the per-channel constant table
 
 struct AUParams {
   const float* x;            // [B, T, ld] fp32
@@ -81,14 +78,13 @@ struct AUTaps {
 };
 __constant__ AUTaps c_au_taps;   // ONE filter per device and process (the first one seen); units with other taps run layer by layer
 
-// snake(u) = u + hb - hb * cos(2 a u), hb = 0.5 / b.  The FIR accumulators start at hb (u' = u + hb), the cosine argument is
-// z = 2a * u' + (pi - 2a * hb) = 2 a u + pi, and cos(z) = -cos(2 a u): v = u' + hb * cos(z) - no negated copy of hb in registers.
 struct SnakeC {
-  f32x2 hb, a2, na2hb;
+  f32x2 hb, nhb, a2, na2hb;
   __device__ __forceinline__ void init(float a0, float a1, float ib0, float ib1) {
     hb = pk2(0.5f * ib0, 0.5f * ib1);
+    nhb = pk2(-0.5f * ib0, -0.5f * ib1);
     a2 = pk2(2.0f * a0, 2.0f * a1);
-    na2hb = pk2(3.14159265358979f - 2.0f * a0 * 0.5f * ib0, 3.14159265358979f - 2.0f * a1 * 0.5f * ib1);
+    na2hb = pk2(-2.0f * a0 * 0.5f * ib0, -2.0f * a1 * 0.5f * ib1);
   }
 };
 
@@ -129,8 +125,8 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) 
     float zo0_, zo1_, ze0_, ze1_;                                                  \
     upk2(fma2(sn.a2, uo_, sn.na2hb), zo0_, zo1_);                                  \
     upk2(fma2(sn.a2, ue_, sn.na2hb), ze0_, ze1_);                                  \
-    V[(2 * (S) + 10) % 12] = fma2(sn.hb, pk2(__cosf(zo0_), __cosf(zo1_)), uo_);   \
-    V[(2 * (S) + 11) % 12] = fma2(sn.hb, pk2(__cosf(ze0_), __cosf(ze1_)), ue_);   \
+    V[(2 * (S) + 10) % 12] = fma2(sn.nhb, pk2(__cosf(zo0_), __cosf(zo1_)), uo_);   \
+    V[(2 * (S) + 11) % 12] = fma2(sn.nhb, pk2(__cosf(ze0_), __cosf(ze1_)), ue_);   \
   }
 // y[t] of the same step: the 12-tap decimating FIR as two independent 6-term chains (even / odd taps)
 #define AU_STEP_DOWN(S, YOUT)                                                      \
@@ -222,11 +218,11 @@ __device__ __noinline__ void au_a1_phase(const A1Args a) {
     }
     return v;
   };
-  f32x2 X[6], V[12], R[3];                               // R: the rows of the next 3 steps, in flight
+  f32x2 X[6], V[12], R[6];
 #pragma unroll
   for (int i = 0; i < 5; ++i) X[i] = ldx();
 #pragma unroll
-  for (int i = 0; i < 3; ++i) R[i] = ldx();
+  for (int i = 0; i < 6; ++i) R[i] = ldx();
   X[5] = pk2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 12; ++i) V[i] = pk2(0.f, 0.f);
@@ -236,8 +232,8 @@ __device__ __noinline__ void au_a1_phase(const A1Args a) {
   // one body = 6 steps; OUT: the steps produce outputs (all bodies but the first), LOAD: the next body's rows are fetched
 #define AU_A1_BODY(OUT, LOAD)                                                                       \
   _Pragma("unroll") for (int s = 0; s < 6; ++s) {                                                   \
-    const f32x2 xin = R[s % 3];                                                                     \
-    if (LOAD || s < 3) R[s % 3] = ldx();                                                            \
+    const f32x2 xin = R[s];                                                                         \
+    if (LOAD) R[s] = ldx();                                                                         \
     AU_STEP_UP(s, xin)                                                                              \
     if (OUT) {                                                                                      \
       f32x2 y;                                                                                      \
@@ -429,7 +425,7 @@ __device__ __noinline__ void au_a2_patch(uint32_t lanebase, int T, int tA2, int 
 //   operand tile is free once conv2 has completed) - the transposition that makes the stream contiguous;
 //   every thread then adds bias / residual and stores 16 bytes per instruction.
 // Tiles whose fp32 block exceeds the operand tile's bytes run in passes of NP columns.
-constexpr int AU_ST_ITEMS = (11 * 256 + AU_CTHREADS - 1) / AU_CTHREADS;   // float4 items per thread and pass (<= 45 KB per pass)
+constexpr int AU_ST_ITEMS = 11;        // float4 items per thread and pass (256 threads: <= 45 KB per pass)
 struct STArgs {
   const float* xblk;     // x rows of this tile (block start)
   void* oblk;            // out rows (fp32 or bf16 elements)
@@ -533,45 +529,41 @@ __device__ __noinline__ void au_store_phase(const STArgs a) {
   }
 }
 
+#ifdef AU_DBG
+// debug builds (BVG_EXTRA_FLAGS=-DAU_DBG): cycles CTA 0 / warp 0 spends in each phase, summed over its tiles
+__device__ long long au_dbg_cycles[8];
+#define AU_T(i) if (dbgw) { const long long now_ = clock64(); au_dbg_cycles[i] += now_ - tprev_; tprev_ = now_; }
+#else
+#define AU_T(i)
+#endif
+
 // ------------------------------------------------------------------------------------------------ kernel
-// ONE CTA per SM runs TWO tile streams (X: its even tiles, Y: its odd tiles), each with its own operand tile in shared
-// memory and its own 256-column TMEM accumulator.  All 16 compute warps execute the same phase together and the phases of
-// the two streams alternate, so that every tcgen05 convolution runs in the background of the other stream's FP32 phase:
-//
-//   compute warps :  A1(X) | ST(Y') | A1(Y) | A2(X) | A2(Y) | ST(X) | A1(X+) | ST(Y) | ...        (Y' = previous pair)
-//   tensor pipe   :         conv1(X) ......   conv1(Y)  conv2(X)  conv2(Y)  ...
-//
-// The first version ran one stream per CTA with two CTAs per SM: ncu showed its compute warps 32 % of the time at the
-// barriers in front of the two convolutions (only the other CTA's 8 warps computing meanwhile), issue slots 42 % used.
-__global__ void __launch_bounds__(AU_THREADS, 1)
+__global__ void __launch_bounds__(AU_THREADS, 2)
 amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                 const __grid_constant__ AUParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* ring = smem;
-  unsigned char* tile0 = smem + p.nslot * p.slotb;
-  const uint32_t tileb = (uint32_t)(p.nch * p.chb);                 // bytes of one stream's operand tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tile0 + 2 * tileb);
+  unsigned char* tile = smem + p.nslot * p.slotb;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tile + p.nch * p.chb);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + AU_MAX_SLOTS;
-  uint64_t* a1_ready = bars + 2 * AU_MAX_SLOTS;                     // [stream]
-  uint64_t* acc1_full = a1_ready + 2;
-  uint64_t* a2_ready = a1_ready + 4;
-  uint64_t* acc2_full = a1_ready + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a1_ready + 8);
+  uint64_t* a1_ready = bars + 2 * AU_MAX_SLOTS;
+  uint64_t* acc1_full = a1_ready + 1;
+  uint64_t* a2_ready = a1_ready + 2;
+  uint64_t* acc2_full = a1_ready + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a1_ready + 4);
   // per-channel constants: [0] exp(alpha1), [1] 1/(exp(beta1)+1e-9), [2] / [3] the same of the second activation, [4] bias2
-  float* ctab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + AU_BAR_BYTES);
+  float* ctab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 112);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nslot; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&a1_ready[s], AU_CWARPS);
-      mbar_init(&acc1_full[s], 1);
-      mbar_init(&a2_ready[s], AU_CWARPS);
-      mbar_init(&acc2_full[s], 1);
-    }
+    mbar_init(a1_ready, AU_CWARPS);
+    mbar_init(acc1_full, 1);
+    mbar_init(a2_ready, AU_CWARPS);
+    mbar_init(acc2_full, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmap_w1);
     tma_prefetch_desc(&tmap_w2);
@@ -591,36 +583,28 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // this CTA's j-th tile is blockIdx.x + j * gridDim.x; pair `it` = tiles 2 it (stream X) and 2 it + 1 (stream Y)
-  const int64_t gstep = gridDim.x;
-  const int64_t my_tiles = p.n_tiles > (int64_t)blockIdx.x ? (p.n_tiles - blockIdx.x + gstep - 1) / gstep : 0;
-  const int64_t n_pairs = (my_tiles + 1) / 2;
 
   if (warp == AU_CWARPS) {
-    // ------------------------------------------------ weight tiles through the ring, in the MMA warp's job order:
-    // conv1(X), conv1(Y), conv2(X), conv2(Y); plus an L2 prefetch of the NEXT pair's x rows
+    // ------------------------------------------------ weight tiles of conv1 then conv2, every tile, through the ring;
+    // plus an L2 prefetch of the NEXT tile's x rows (phase A1 then reads them at L2 latency)
     const uint32_t w_bytes = (uint32_t)p.wrows * 128u;
     uint32_t ws = 0, wph = 0;
     const int span = p.NSEG1 * p.L1 + 12;
-    for (int64_t it = 0; it < n_pairs; ++it) {
-      const int nstream = (2 * it + 1 < my_tiles) ? 2 : 1;
-      for (int s = 0; s < 2; ++s) {
-        const int64_t j = 2 * (it + 1) + s;
-        if (j < my_tiles && elect_one()) {
-          const int64_t nxt = blockIdx.x + j * gstep;
-          const int nb = (int)(nxt / p.n_ttiles);
-          const int nt0 = (int)(nxt % p.n_ttiles) * p.NOUT;
-          int ta = nt0 - p.h2 - 6 - p.h1 - 6;
-          int tb = ta + span;
-          if (ta < 0) ta = 0;
-          if (tb > p.T) tb = p.T;
-          if (tb > ta)
-            l2_prefetch_bulk(p.x + ((int64_t)nb * p.T + ta) * p.ld, (uint32_t)((int64_t)(tb - ta) * p.ld * 4));
-        }
-        __syncwarp();
+    for (int64_t tile_i = blockIdx.x; tile_i < p.n_tiles; tile_i += gridDim.x) {
+      const int64_t nxt = tile_i + gridDim.x;
+      if (nxt < p.n_tiles && elect_one()) {
+        const int nb = (int)(nxt / p.n_ttiles);
+        const int nt0 = (int)(nxt % p.n_ttiles) * p.NOUT;
+        int ta = nt0 - p.h2 - 6 - p.h1 - 6;
+        int tb = ta + span;
+        if (ta < 0) ta = 0;
+        if (tb > p.T) tb = p.T;
+        if (tb > ta)
+          l2_prefetch_bulk(p.x + ((int64_t)nb * p.T + ta) * p.ld, (uint32_t)((int64_t)(tb - ta) * p.ld * 4));
       }
-      for (int job = 0; job < 2 * nstream; ++job) {
-        const CUtensorMap* tm = (job >= nstream) ? &tmap_w2 : &tmap_w1;
+      __syncwarp();
+      for (int conv = 0; conv < 2; ++conv) {
+        const CUtensorMap* tm = conv ? &tmap_w2 : &tmap_w1;
         for (int j = 0; j < p.k; ++j) {
           for (int c = 0; c < p.nch; ++c) {
             mbar_wait_sleep(&w_empty[ws], wph ^ 1, 100);
@@ -640,19 +624,16 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
     const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t desc0 = make_smem_desc(0, 128, 0);
     const uint32_t dhi = (uint32_t)(desc0 >> 32);
-    const uint32_t a_lo0 = (uint32_t)desc0 + (smem_u32(ring) >> 4), b_lo0 = (uint32_t)desc0 + (smem_u32(tile0) >> 4);
-    const uint32_t slot16 = (uint32_t)p.slotb >> 4, ch16 = (uint32_t)p.chb >> 4, tile16 = tileb >> 4;
-    uint32_t ws = 0, wph = 0;
-    for (int64_t it = 0; it < n_pairs; ++it) {
-      const uint32_t ph = (uint32_t)it & 1u;
-      const int nstream = (2 * it + 1 < my_tiles) ? 2 : 1;
-      for (int job = 0; job < 2 * nstream; ++job) {
-        const int conv = job >= nstream ? 1 : 0, s = job - conv * nstream;
-        mbar_wait_sleep(conv ? &a2_ready[s] : &a1_ready[s], ph, 60);
+    const uint32_t a_lo0 = (uint32_t)desc0 + (smem_u32(ring) >> 4), b_lo0 = (uint32_t)desc0 + (smem_u32(tile) >> 4);
+    const uint32_t slot16 = (uint32_t)p.slotb >> 4, ch16 = (uint32_t)p.chb >> 4;
+    uint32_t ws = 0, wph = 0, it = 0;
+    for (int64_t tile_i = blockIdx.x; tile_i < p.n_tiles; tile_i += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      for (int conv = 0; conv < 2; ++conv) {
+        mbar_wait_sleep(conv ? a2_ready : a1_ready, ph, 60);
         tc_fence_after();
         const uint32_t idesc = conv ? idesc2 : idesc1;
         const uint32_t tap_step = (uint32_t)((conv ? 1 : p.dil) * 8);
-        const uint32_t acc = tmem_base + (uint32_t)s * AU_ACC_COLS;
         uint32_t accum = 0;
         for (int j = 0; j < p.k; ++j) {
           for (int c = 0; c < p.nch; ++c) {
@@ -661,11 +642,11 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
             mbar_wait(&w_full[ws], wph);
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + ws * slot16;
-            const uint32_t b_lo = b_lo0 + (uint32_t)s * tile16 + (uint32_t)c * ch16 + (uint32_t)j * tap_step;
+            const uint32_t b_lo = b_lo0 + (uint32_t)c * ch16 + (uint32_t)j * tap_step;
             if (elect_one()) {
               const uint64_t da = ((uint64_t)dhi << 32) | a_lo, db = ((uint64_t)dhi << 32) | b_lo;
-              umma_f16_ss(acc, da, db, idesc, accum);
-              for (int q = 1; q < nkk; ++q) umma_f16_ss(acc, da + 2 * q, db + 2 * q, idesc, 1u);
+              umma_f16_ss(tmem_base, da, db, idesc, accum);
+              for (int q = 1; q < nkk; ++q) umma_f16_ss(tmem_base, da + 2 * q, db + 2 * q, idesc, 1u);
               umma_commit(&w_empty[ws]);
             }
             __syncwarp();
@@ -673,43 +654,37 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
             if (++ws == (uint32_t)p.nslot) { ws = 0; wph ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(conv ? &acc2_full[s] : &acc1_full[s]);
+        if (elect_one()) umma_commit(conv ? acc2_full : acc1_full);
         __syncwarp();
       }
     }
   } else {
-    // ------------------------------------------------ compute warps 0..15
+    // ------------------------------------------------ compute warps 0..7
     const int tid = threadIdx.x;
-    const uint32_t tile_u32_0 = smem_u32(tile0);
+    const uint32_t tile_u32 = smem_u32(tile);
     // tile-invariant: the phase-A1 (pair, segment) of this thread, the lane's channel and role in the TMEM phases
     const int seg1 = tid / p.P, pair1 = tid - seg1 * p.P;
-    const int g = warp & 3, share = warp >> 2;             // TMEM lane quadrant, this warp's index among the quadrant's warps
+    const int g = warp & 3, half = warp >> 2;
     const int lane0 = (g * 32) % p.LR, replica = (g * 32) / p.LR;
     const int chT = lane0 + lane;
     const bool warp_ok = lane0 < p.Cp;
     const bool lane_ok = warp_ok && chT < p.Cp;
-    const int segT = replica * AU_SHARE + share;           // which share of a channel group's rows / columns this warp takes
+    const int segT = replica * 2 + half;                 // which share of a channel group's rows / columns this warp takes
     const float bv1 = lane_ok ? __ldg(p.bias1 + chT) : 0.f;
-    const float a2a = lane_ok ? ctab[2 * p.Cp + chT] : 1.f, a2ib = lane_ok ? ctab[3 * p.Cp + chT] : 1.f;
-
-    struct TileId { int b, t0; };
-    auto tile_of = [&](int64_t j) -> TileId {
-      const int64_t ti = blockIdx.x + j * gstep;
-      TileId t;
-      t.b = (int)(ti / p.n_ttiles);
-      t.t0 = (int)(ti % p.n_ttiles) * p.NOUT;
-      return t;
-    };
-    auto is_interior = [&](int t0) -> bool {
-      const int tA1 = t0 - p.h2 - 6 - p.h1;
-      return tA1 - 6 >= 0 && tA1 + p.NSEG1 * p.L1 + 5 <= p.T - 1;
-    };
-    // phase A1 of stream s: x -> operand tile s, then hand the tile to the MMA warp
-    auto phase_a1 = [&](int s, TileId t) {
-      const uint32_t tile_u32 = tile_u32_0 + (uint32_t)s * tileb;
-      const int tA1 = t.t0 - p.h2 - 6 - p.h1;
-      const bool interior = is_interior(t.t0);
-      const float* xu = p.x + (int64_t)t.b * p.T * p.ld;
+    const uint32_t lanebase = tmem_base + ((uint32_t)(g * 32) << 16);
+    uint32_t it = 0;
+#ifdef AU_DBG
+    const bool dbgw = blockIdx.x == 0 && threadIdx.x == 0;
+    long long tprev_ = clock64();
+#endif
+    for (int64_t tile_i = blockIdx.x; tile_i < p.n_tiles; tile_i += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const int b = (int)(tile_i / p.n_ttiles);
+      const int t0 = (int)(tile_i % p.n_ttiles) * p.NOUT;
+      const int tA2 = t0 - p.h2;
+      const int tA1 = tA2 - 6 - p.h1;
+      const bool interior = tA1 - 6 >= 0 && tA1 + p.NSEG1 * p.L1 + 5 <= p.T - 1;
+      const float* xu = p.x + (int64_t)b * p.T * p.ld;
       if (seg1 < p.NSEG1) {
         const int c0 = 2 * pair1, kk = c0 & 63;
         A1Args a;
@@ -736,18 +711,14 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a1_ready[s]);
-    };
-    // phase A2 of stream s: accumulator s (conv1) -> operand tile s (conv1 has finished reading it), hand it to the MMA warp
-    auto phase_a2 = [&](int s, TileId t, uint32_t ph) {
-      const uint32_t tile_u32 = tile_u32_0 + (uint32_t)s * tileb;
-      const uint32_t lanebase = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)s * AU_ACC_COLS;
-      const int tA2 = t.t0 - p.h2;
-      const bool interior = is_interior(t.t0);
+      AU_T(0)
+      if (lane == 0) mbar_arrive(a1_ready);
       // conv1 complete: ONE warp watches the mbarrier, the others park on a hardware barrier (no issue slots spent)
-      if (warp == 0) mbar_wait_sleep(&acc1_full[s], ph, 40);
+      if (warp == 0) mbar_wait_sleep(acc1_full, ph, 40);
       named_bar_sync(2, AU_CTHREADS);
       tc_fence_after();
+      AU_T(1)
+      const float a2a = lane_ok ? ctab[2 * p.Cp + chT] : 1.f, a2ib = lane_ok ? ctab[3 * p.Cp + chT] : 1.f;
       if (warp_ok) {
         const int kk = chT & 63;
         A2Args a;
@@ -761,53 +732,33 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
       if (!interior) {
         named_bar_sync(1, AU_CTHREADS);
         if (warp_ok)
-          au_a2_patch(lanebase, p.T, tA2, p.R2T, segT, AU_SHARE * p.rep, tile_u32, p.chb, chT, lane_ok, a2a, a2ib, bv1);
+          au_a2_patch(lanebase, p.T, tA2, p.R2T, segT, 2 * p.rep, tile_u32, p.chb, chT, lane_ok, a2a, a2ib, bv1);
       }
       tmem_ld_wait();
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a2_ready[s]);
-    };
-    // phase ST of stream s (waits for conv2 inside, after its residual loads are in flight)
-    auto phase_st = [&](int s, TileId t, uint32_t ph) {
-      const uint32_t tile_u32 = tile_u32_0 + (uint32_t)s * tileb;
-      const uint32_t lanebase = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)s * AU_ACC_COLS;
-      int nv = p.T - t.t0;
-      if (nv > p.NOUT) nv = p.NOUT;
-      const int64_t o0 = ((int64_t)t.b * p.T + t.t0) * p.ld;
-      STArgs a;
-      a.xblk = p.x + o0;
-      a.oblk = p.out_bf16 ? (void*)(reinterpret_cast<__nv_bfloat16*>(p.out) + o0) : (void*)(reinterpret_cast<float*>(p.out) + o0);
-      a.ablk = p.accum ? p.accum + o0 : nullptr;
-      a.n4 = nv * (p.Cp >> 2); a.np4 = p.NPst * (p.Cp >> 2); a.NP = p.NPst; a.NV = nv; a.Cp = p.Cp;
-      a.stg = tile_u32; a.bias_s = smem_u32(ctab + 4 * p.Cp); a.sc = p.scale; a.obf = p.out_bf16;
-      a.lanebase = lanebase; a.ch = chT; a.lane_ok = lane_ok; a.warp_ok = warp_ok; a.me = segT; a.nshare = AU_SHARE * p.rep;
-      a.bar = &acc2_full[s]; a.ph = ph; a.tid = tid;
-      au_store_phase(a);
+      AU_T(2)
+      if (lane == 0) mbar_arrive(a2_ready);
+      // phase ST (waits for conv2 inside, after its residual loads are in flight)
+      {
+        int nv = p.T - t0;
+        if (nv > p.NOUT) nv = p.NOUT;
+        const int64_t o0 = ((int64_t)b * p.T + t0) * p.ld;
+        STArgs a;
+        a.xblk = p.x + o0;
+        a.oblk = p.out_bf16 ? (void*)(reinterpret_cast<__nv_bfloat16*>(p.out) + o0) : (void*)(reinterpret_cast<float*>(p.out) + o0);
+        a.ablk = p.accum ? p.accum + o0 : nullptr;
+        a.n4 = nv * (p.Cp >> 2); a.np4 = p.NPst * (p.Cp >> 2); a.NP = p.NPst; a.NV = nv; a.Cp = p.Cp;
+        a.stg = tile_u32; a.bias_s = smem_u32(ctab + 4 * p.Cp); a.sc = p.scale; a.obf = p.out_bf16;
+        a.lanebase = lanebase; a.ch = chT; a.lane_ok = lane_ok; a.warp_ok = warp_ok; a.me = segT; a.nshare = 2 * p.rep;
+        a.bar = acc2_full; a.ph = ph; a.tid = tid;
+        au_store_phase(a);
+      }
       tmem_ld_wait();
       tc_fence_before();
-    };
-
-    TileId prevY;
-    prevY.b = 0; prevY.t0 = 0;
-    bool have_prevY = false;
-    for (int64_t it = 0; it < n_pairs; ++it) {
-      const uint32_t ph = (uint32_t)it & 1u;
-      const bool haveY = 2 * it + 1 < my_tiles;
-      const TileId tx = tile_of(2 * it);
-      TileId ty = tx;
-      if (haveY) ty = tile_of(2 * it + 1);
-      phase_a1(0, tx);
-      if (have_prevY) phase_st(1, prevY, ph ^ 1u);        // conv2(Y') has had ST(X') and A1(X) to complete
-      if (haveY) phase_a1(1, ty);
-      phase_a2(0, tx, ph);
-      if (haveY) phase_a2(1, ty, ph);
-      phase_st(0, tx, ph);
-      prevY = ty;
-      have_prevY = haveY;
+      AU_T(4)
     }
-    if (have_prevY) phase_st(1, prevY, (uint32_t)(n_pairs - 1) & 1u);
   }
 
   tc_fence_before();
@@ -839,13 +790,13 @@ static bool au_plan(const AmpUnitArgs& a, AUParams& p) {
   if (p.rep > 1 && weight_replica_rows(a.Cp, 128) != p.LR) return false;
   p.wrows = p.rep == 1 ? round_up(a.Cp, 8) : 128;
   p.slotb = round_up(p.wrows * 128, 1024);
-  p.nslot = 3;                                            // at least; grown below into what the two tiles leave
-  int rbmax = (AU_MAX_SMEM - 1024 - AU_TAIL_BYTES - p.nslot * p.slotb) / 2 / (p.nch * 128) / 8 * 8;
+  p.nslot = p.nch == 2 ? 3 : 4;
+  int rbmax = (AU_MAX_SMEM - 1024 - AU_TAIL_BYTES - p.nslot * p.slotb) / (p.nch * 128) / 8 * 8;
   if (rbmax > 320) rbmax = 320;
   int n1max = (rbmax - 2 * p.h1) / 16 * 16;
-  if (n1max > AU_ACC_COLS) n1max = AU_ACC_COLS;
+  if (n1max > 256) n1max = 256;
   if (n1max < 64) return false;
-  const int nss = 2 * AU_SHARE * p.rep;                   // a2 sub-segments per channel group (two per warp)
+  const int nss = 4 * p.rep;
   p.L2 = (n1max - 11) / nss / 6 * 6;
   if (p.L2 < 6) return false;
   p.R2T = nss * p.L2;
@@ -862,7 +813,6 @@ static bool au_plan(const AmpUnitArgs& a, AUParams& p) {
   p.RB = round_up(p.R1 > p.R2T ? p.R1 : p.R2T, 8);
   if (p.RB > rbmax) return false;
   p.chb = round_up(p.RB * 128, 1024);
-  while (p.nslot < AU_MAX_SLOTS && 1024 + (p.nslot + 1) * p.slotb + 2 * p.nch * p.chb + AU_TAIL_BYTES <= AU_MAX_SMEM) ++p.nslot;
   {
     // phase ST stages the tile's fp32 block in the operand tile: passes of NPst columns, <= AU_ST_ITEMS float4 per thread
     int cap = p.nch * p.chb;
@@ -873,7 +823,7 @@ static bool au_plan(const AmpUnitArgs& a, AUParams& p) {
   }
   p.n_ttiles = (int)ceil_div(a.T, p.NOUT);
   p.n_tiles = (int64_t)a.B * p.n_ttiles;
-  if (1024 + p.nslot * p.slotb + 2 * p.nch * p.chb + AU_TAIL_BYTES > AU_MAX_SMEM) return false;
+  if (1024 + p.nslot * p.slotb + p.nch * p.chb + AU_TAIL_BYTES > AU_MAX_SMEM) return false;
   return true;
 }
 
@@ -915,7 +865,7 @@ int amp_unit_launch(const AmpUnitArgs& a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_map_any(&m2, a.w2, 2, (uint64_t)a.Cp, 128, (uint64_t)a.k, (uint64_t)a.Cp, 64, (uint32_t)p.wrows, 1, 128);
   if (rc) return rc;
-  const int smem = 1024 + p.nslot * p.slotb + 2 * p.nch * p.chb + AU_TAIL_BYTES;
+  const int smem = 1024 + p.nslot * p.slotb + p.nch * p.chb + AU_TAIL_BYTES;
   // kernel attributes are per device: set once for each
   static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
@@ -926,9 +876,26 @@ int amp_unit_launch(const AmpUnitArgs& a, cudaStream_t st) {
     if (dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_release);
   }
   const int sms = umma_sm_count();
-  const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
+  const unsigned grid = (unsigned)(p.n_tiles < 2 * sms ? p.n_tiles : 2 * sms);
+#ifdef AU_DBG
+  {
+    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbolAsync(au_dbg_cycles, z, sizeof(z), 0, cudaMemcpyHostToDevice, st);
+  }
+#endif
   amp_unit_kernel<<<grid, AU_THREADS, smem, st>>>(m1, m2, p);
   BVG_LAUNCHED();
+#ifdef AU_DBG
+  {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, au_dbg_cycles, sizeof(h));
+    const long long tiles0 = (p.n_tiles + grid - 1) / grid;
+    fprintf(stderr, "audbg Cp=%d k=%d dil=%d N1=%d NOUT=%d L1=%d NSEG1=%d L2=%d tiles/cta=%lld | per tile: a1 %.0f  wait-mma1 %.0f  a2 %.0f  store (incl. wait for conv2) %.0f\n",
+            p.Cp, p.k, p.dil, p.N1, p.NOUT, p.L1, p.NSEG1, p.L2, tiles0, (double)h[0] / tiles0, (double)h[1] / tiles0,
+            (double)h[2] / tiles0, (double)h[4] / tiles0);
+  }
+#endif
   return BVG_OK;
 }
 
