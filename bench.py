@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--act-sweep", action="store_true", help="include the full fused-activation HBM sweep table (config 3)")
     ap.add_argument("--no-act-sweep", action="store_true", help="skip the activation sweep summary")
-    ap.add_argument("--no-extras", action="store_true", help="headline numbers only (no precision modes, sweep, latency table)")
+    ap.add_argument("--no-extras", action="store_true", help="headline numbers only (no precision modes, activation sweep, single-utterance latency)")
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 256 if a.workload == "c4" else 16
@@ -476,7 +476,7 @@ def main():
         # ---- latency of ONE utterance, the way infer_v2 calls the vocoder (batch 1, one segment): 2 s (BASELINE
         #      configs[0] shape) and 10 s, repeated shapes (CUDA-graph replay after the first call of a shape) ----
         latency = {}
-        if not c4:
+        if extras:
             for frames in (172, 861):
                 mel1 = mel[:1, :, :frames].contiguous() if T0 >= frames else None
                 if mel1 is None:
