@@ -494,6 +494,46 @@ def main():
                 latency[frames] = {"frames": frames, "audio_s": frames * HOP / SR, "ms": ms_one,
                                    "x_realtime": frames * HOP / SR / (ms_one * 1e-3)}
 
+        # ---- BASELINE configs[4], vocoder side: the segment loop of infer_v2.py:616-744 replayed around the drop-in (GPT and
+        #      s2mel are out of scope and cannot be imported here): per text segment `wav = self.bigvgan(vc_target.float())`,
+        #      `torch.clamp(32767 * wav, -32767, 32767)`, `wav.cpu()`; wall clock like the reference's own `bigvgan_time` ----
+        replay = None
+        if extras and rank == 0:
+            seg_frames = [388, 517, 301, 646, 431, 560, 258, 474, 905, 1290]      # 10 segments, 3-15 s (<= 1500 mel tokens each)
+            segs = [synth.make_mel(1, h["num_mels"], f, first_utterance=100 + i).to(dev) for i, f in enumerate(seg_frames)]
+            segs_host = [vc.cpu().pin_memory() for vc in segs]
+            audio = sum(seg_frames) * HOP / SR
+
+            def loop_reference_form():
+                wavs = []
+                for vc_target in segs:
+                    wav = model(vc_target.float()).squeeze().unsqueeze(0)
+                    wav = torch.clamp(32767 * wav, -32767.0, 32767.0)
+                    wavs.append(wav.cpu())
+                return wavs
+
+            def loop_host_int16():
+                return [model.forward_host(vc, int16=True) for vc in segs_host]     # pinned host mel in, int16 host waveform out
+
+            def timed(fn, n=5):
+                fn(); fn()
+                ts = []
+                for _ in range(n):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    fn()
+                    torch.cuda.synchronize()
+                    ts.append(time.perf_counter() - t0)
+                return median(ts)
+            t_ref_form = timed(loop_reference_form)
+            t_i16 = timed(loop_host_int16)
+            t_batched = timed(lambda: [w.cpu() for w in model.forward_segments(segs)])
+            replay = {"segments": len(seg_frames), "frames": seg_frames, "audio_s": audio,
+                      "loop_as_infer_v2": {"bigvgan_time_s": t_ref_form, "rtf": t_ref_form / audio, "x_realtime": audio / t_ref_form},
+                      "loop_forward_host_int16": {"bigvgan_time_s": t_i16, "rtf": t_i16 / audio, "x_realtime": audio / t_i16},
+                      "forward_segments_one_call": {"bigvgan_time_s": t_batched, "rtf": t_batched / audio, "x_realtime": audio / t_batched},
+                      "note": "vocoder stage only (GPT + s2mel out of scope); median of 5 wall-clock passes after 2 warm-ups"}
+
     value = audio_s_step * args.steps / (ms * 1e-3)
     e2e_measured = audio_s_step * args.steps / e2e_s
     # the end-to-end pass does strictly more work per step (the same kernels plus the two PCIe copies); when its median
@@ -571,6 +611,8 @@ def main():
                             "ms_per_step": ms_serial / args.steps, "bit_identical_to_default": serial_identical,
                             "note": "bvg_set_option('streams', 1); the default runs the 3 AMP blocks of a stage on 3 streams"},
     }
+    if replay:
+        out["infer_v2_segment_replay"] = replay
     if 172 in latency:
         out["single_utterance"] = latency[172]
     if 861 in latency:
