@@ -176,3 +176,22 @@ def test_bench_reference_arm_prints_contract_json():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "audio-s/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_arms_share_config_and_metric():
+    """the reference arm reports on the SAME `config`, metric and unit as the GPU arm (it times a bounded sample of it), for both
+    workloads; `--workload c4` is the 256 x 30 s strong-scaling case of BASELINE configs[3]"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import argparse
+    for wl, batch, frames in (("headline", 16, 861), ("c4", 256, 2584)):
+        a = argparse.Namespace(workload=wl, batch=batch, frames=frames)
+        c1, c8 = bench.workload_config(a, 1), bench.workload_config(a, 8)
+        assert c1["workload"] == c8["workload"] and "model" not in c1
+        assert c1["global_batch"] == batch and c8["global_batch"] == (batch if wl == "c4" else 8 * batch)
+    rows = [{"impl": "ours", "dtype": "bfloat16", "snake": "fast", "T": T, "frac_hbm": f, "GBps": 6547.8 * f}
+            for T, f in ((8192, 0.3), (131072, 0.4), (2097152, 0.5))]
+    s = bench.act_sweep_summary(rows, {"hbm_gbs": 6547.8})["series"]["ours bfloat16 fast"]
+    assert s["frac_min"] == 0.3 and s["frac_max"] == 0.5 and s["frac_median"] == 0.4 and s["frac_median_T_ge_131072"] == 0.5

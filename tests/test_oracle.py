@@ -139,6 +139,24 @@ def test_oracle_matches_live_reference(synth, cfg):
     assert set(m.state_dict().keys()) == set(sd.keys())
 
 
+def test_staged_form_is_the_reference_operator_sequence(synth, cfg):
+    """`O.staged_ops()` (the form bench.py times as the CPU arm) runs every Activation1d as the literal F.pad / conv_transpose1d /
+    conv1d sequence of the reference: equal to the closed polyphase form to rounding, and - with the reference mounted -
+    BIT-identical to the reference's own forward (same torch ops in the same order)."""
+    h = cfg.tiny_hparams()
+    sd = synth.make_state_dict(h, seed=5)
+    mel = synth.make_mel(2, h["num_mels"], 17)
+    closed = O.generator_forward(sd, h, mel)
+    with O.staged_ops():
+        staged = O.generator_forward(sd, h, mel)
+    assert not O._STAGED
+    assert (staged - closed).abs().max() <= 2e-6
+    if refshim.available():
+        with torch.no_grad():
+            ref = refshim.build_generator(h, sd)(mel)
+        assert torch.equal(staged, ref)
+
+
 # ---- IndexTTS-v1 speaker-conditioned generator (SURVEY.md 8(f) rank 2) ------------------------------------------
 V1_CASES = {
     "v1_tiny": lambda cfg: cfg.tiny_v1_hparams(),
