@@ -22,10 +22,10 @@ namespace bvg {
 // 8 pad channels right behind a channel pair (row pitch = channels + 8): exact zeros, so that the zero weight columns of the
 // next conv never meet a stale NaN bit pattern.  Issued by the thread that owns the LAST real pair, at a constant offset.
 __device__ __forceinline__ void store_pad8(float* p) {
-  BVG_STG(reinterpret_cast<float4*>(p + 2), make_float4(0.f, 0.f, 0.f, 0.f));
-  BVG_STG(reinterpret_cast<float4*>(p + 6), make_float4(0.f, 0.f, 0.f, 0.f));
+  *(reinterpret_cast<float4*>(p + 2)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *(reinterpret_cast<float4*>(p + 6)) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
-__device__ __forceinline__ void store_pad8(__nv_bfloat16* p) { BVG_STG(reinterpret_cast<uint4*>(p + 2), make_uint4(0u, 0u, 0u, 0u)); }
+__device__ __forceinline__ void store_pad8(__nv_bfloat16* p) { *(reinterpret_cast<uint4*>(p + 2)) = make_uint4(0u, 0u, 0u, 0u); }
 
 
 template <typename T, int VEC>
@@ -33,7 +33,7 @@ struct VecIO;
 template <>
 struct VecIO<float, 1> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = BVG_LDG(p); }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { BVG_STG(p, v[0]); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *(p) = v[0]; }
 };
 template <>
 struct VecIO<float, 2> {
@@ -43,7 +43,7 @@ struct VecIO<float, 2> {
     v[1] = t.y;
   }
   static __device__ __forceinline__ void store(float* p, const float (&v)[2]) {
-    BVG_STG(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+    *(reinterpret_cast<float2*>(p)) = make_float2(v[0], v[1]);
   }
 };
 template <>
@@ -52,7 +52,7 @@ struct VecIO<__nv_bfloat16, 1> {
     v[0] = ld_mut_f32<__nv_bfloat16>(p);
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) {
-    BVG_STG(reinterpret_cast<unsigned short*>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v[0])));
+    *(reinterpret_cast<unsigned short*>(p)) = __bfloat16_as_ushort(__float2bfloat16_rn(v[0]));
   }
 };
 template <>
@@ -64,7 +64,7 @@ struct VecIO<__nv_bfloat16, 2> {
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[2]) {
     const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-    BVG_STG(reinterpret_cast<unsigned int*>(p), *reinterpret_cast<const unsigned int*>(&h2));
+    *(reinterpret_cast<unsigned int*>(p)) = *reinterpret_cast<const unsigned int*>(&h2);
   }
 };
 
@@ -231,7 +231,6 @@ act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float
                 int nseg, int nseg_head, int64_t tail_start, int64_t nitems) {
   act1d_cl_body<Tin, Tout, VEC, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, L, nseg, nseg_head, tail_start, nitems,
                                       (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
-  BVG_EXIT_FENCE();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -250,7 +249,7 @@ template <> struct PairIO<float> {
   static __device__ __forceinline__ f32x2 cvt(raw_t r) { return pk2(r.x, r.y); }
   static __device__ __forceinline__ void store(float* p, f32x2 v) {
     float a, b; upk2(v, a, b);
-    BVG_STG(reinterpret_cast<float2*>(p), make_float2(a, b));
+    *(reinterpret_cast<float2*>(p)) = make_float2(a, b);
   }
 };
 template <> struct PairIO<__nv_bfloat16> {
@@ -260,7 +259,7 @@ template <> struct PairIO<__nv_bfloat16> {
   static __device__ __forceinline__ void store(__nv_bfloat16* p, f32x2 v) {
     float a, b; upk2(v, a, b);
     const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-    BVG_STG(reinterpret_cast<unsigned int*>(p), *reinterpret_cast<const unsigned int*>(&h2));
+    *(reinterpret_cast<unsigned int*>(p)) = *reinterpret_cast<const unsigned int*>(&h2);
   }
 };
 
@@ -310,7 +309,6 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
     // beside the interior blocks instead of as a separate ~10 us launch behind them
     act1d_cl_body<Tin, Tout, 2, FAST, PAD8>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, head_len, nseg_edge, nseg_head, tail_start,
                                       nitems_edge, (int64_t)(blockIdx.x - main_blocks) * blockDim.x + threadIdx.x);
-    BVG_EXIT_FENCE();
     return;
   }
   const int P = C / 2;
@@ -358,7 +356,6 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
       BVG_ACT2_STEP(s, true)
     }
   }
-  BVG_EXIT_FENCE();
 }
 
 // Launch plan: rows [kEdge, kEdge + n_int*L) of every utterance ("interior": no clamps, no edge

@@ -529,13 +529,6 @@ __device__ __noinline__ void au_store_phase(const STArgs a) {
   }
 }
 
-#ifdef AU_DBG
-// debug builds (BVG_EXTRA_FLAGS=-DAU_DBG): cycles CTA 0 / warp 0 spends in each phase, summed over its tiles
-__device__ long long au_dbg_cycles[8];
-#define AU_T(i) if (dbgw) { const long long now_ = clock64(); au_dbg_cycles[i] += now_ - tprev_; tprev_ = now_; }
-#else
-#define AU_T(i)
-#endif
 
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(AU_THREADS, 2)
@@ -673,10 +666,6 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
     const float bv1 = lane_ok ? __ldg(p.bias1 + chT) : 0.f;
     const uint32_t lanebase = tmem_base + ((uint32_t)(g * 32) << 16);
     uint32_t it = 0;
-#ifdef AU_DBG
-    const bool dbgw = blockIdx.x == 0 && threadIdx.x == 0;
-    long long tprev_ = clock64();
-#endif
     for (int64_t tile_i = blockIdx.x; tile_i < p.n_tiles; tile_i += gridDim.x, ++it) {
       const uint32_t ph = it & 1u;
       const int b = (int)(tile_i / p.n_ttiles);
@@ -711,13 +700,11 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
       }
       fence_proxy_async_smem();
       __syncwarp();
-      AU_T(0)
       if (lane == 0) mbar_arrive(a1_ready);
       // conv1 complete: ONE warp watches the mbarrier, the others park on a hardware barrier (no issue slots spent)
       if (warp == 0) mbar_wait_sleep(acc1_full, ph, 40);
       named_bar_sync(2, AU_CTHREADS);
       tc_fence_after();
-      AU_T(1)
       const float a2a = lane_ok ? ctab[2 * p.Cp + chT] : 1.f, a2ib = lane_ok ? ctab[3 * p.Cp + chT] : 1.f;
       if (warp_ok) {
         const int kk = chT & 63;
@@ -738,7 +725,6 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      AU_T(2)
       if (lane == 0) mbar_arrive(a2_ready);
       // phase ST (waits for conv2 inside, after its residual loads are in flight)
       {
@@ -757,7 +743,6 @@ amp_unit_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_consta
       }
       tmem_ld_wait();
       tc_fence_before();
-      AU_T(4)
     }
   }
 
@@ -877,25 +862,8 @@ int amp_unit_launch(const AmpUnitArgs& a, cudaStream_t st) {
   }
   const int sms = umma_sm_count();
   const unsigned grid = (unsigned)(p.n_tiles < 2 * sms ? p.n_tiles : 2 * sms);
-#ifdef AU_DBG
-  {
-    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    cudaMemcpyToSymbolAsync(au_dbg_cycles, z, sizeof(z), 0, cudaMemcpyHostToDevice, st);
-  }
-#endif
   amp_unit_kernel<<<grid, AU_THREADS, smem, st>>>(m1, m2, p);
   BVG_LAUNCHED();
-#ifdef AU_DBG
-  {
-    long long h[8];
-    cudaStreamSynchronize(st);
-    cudaMemcpyFromSymbol(h, au_dbg_cycles, sizeof(h));
-    const long long tiles0 = (p.n_tiles + grid - 1) / grid;
-    fprintf(stderr, "audbg Cp=%d k=%d dil=%d N1=%d NOUT=%d L1=%d NSEG1=%d L2=%d tiles/cta=%lld | per tile: a1 %.0f  wait-mma1 %.0f  a2 %.0f  store (incl. wait for conv2) %.0f\n",
-            p.Cp, p.k, p.dil, p.N1, p.NOUT, p.L1, p.NSEG1, p.L2, tiles0, (double)h[0] / tiles0, (double)h[1] / tiles0,
-            (double)h[2] / tiles0, (double)h[4] / tiles0);
-  }
-#endif
   return BVG_OK;
 }
 

@@ -50,8 +50,9 @@ constexpr int U2_SMEM_USED = 1024 + U2_AIN_SLOTS * U2_SLOT_BYTES + U2_X_STAGES *
                              U2_OUT_SLOTS * U2_SLOT_BYTES + 512;
 // The launch asks for the whole 227 KB opt-in maximum: with the 1 KB the system reserves per CTA that is the SM's entire
 // 228 KB carve-out, so no CTA of any other kernel (not even one without shared memory) can become resident beside this
-// persistent CTA.  Co-resident activation blocks of another stream were the one condition under which older revisions
-// returned corrupted tiles; owning the SM costs nothing and removes the exposure.
+// persistent CTA.  Co-resident blocks of another stream were the condition under which older revisions returned corrupted
+// tiles (root cause: hand-off arrives overtaking unfinished loads, fixed by loads_landed() - DESIGN.md section 7.1); owning
+// the SM costs nothing and stays as a second line of defence.
 constexpr int U2_SMEM_BYTES = 227 * 1024;
 static_assert(U2_SMEM_USED <= U2_SMEM_BYTES, "shared-memory plan exceeds the opt-in maximum");
 
@@ -113,6 +114,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   uint64_t* out_ready = in_free + U2_IN_SLOTS;
   uint64_t* out_free = out_ready + U2_OUT_SLOTS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + U2_OUT_SLOTS);
+  const uint32_t sink_u32 = smem_u32(tmem_slot + 4 + (threadIdx.x / 32));   // one sink word per warp (loads_landed, common.cuh)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
@@ -329,11 +331,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
               for (int i = 0; i < NCOL; ++i) av[i] = ld_shared_f32(ia + acc_off + i * istep);
             }
-            // the loads above are only ISSUED at this point: wait until their values are in registers (common.cuh,
-            // consume16) before the slot is handed back to the TMA producer - an arrive that overtook loads still queued
-            // in a stalled LSU let the refill overwrite rows this warp had not read yet
-            if (NCOL == 16) consume16f(reinterpret_cast<float(&)[16]>(rv)); else consume8f(reinterpret_cast<float(&)[8]>(rv));
-            if (NIN == 2) { if (NCOL == 16) consume16f(reinterpret_cast<float(&)[16]>(av)); else consume8f(reinterpret_cast<float(&)[8]>(av)); }
+            // the loads above are only ISSUED at this point: their values must be in registers before the slot goes back to
+            // the TMA producer (common.cuh, loads_landed)
+            uint32_t h = fold_bits(rv);
+            if (NIN == 2) h ^= fold_bits(av);
+            loads_landed(sink_u32, h);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&in_free[slot]);   // values are in registers: the slot may be refilled
@@ -341,7 +343,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (warp_ok) {
           // same for the accumulator columns before the accumulator can be handed back to the MMA warp below
           tmem_ld_wait();
-          if (NCOL == 16) consume16(reinterpret_cast<uint32_t(&)[16]>(v)); else consume8(reinterpret_cast<uint32_t(&)[8]>(v));
+          loads_landed(sink_u32, fold_bits(v));
         }
         if (nb + CB >= t.nb_end) {           // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();

@@ -310,123 +310,7 @@ static int run_conv_split(bvg_vocoder* v, const ConvW& c, const float* in, Split
   return BVG_OK;
 }
 
-#ifdef BVG_DUAL
-// Debug builds only (BVG_EXTRA_FLAGS=-DBVG_DUAL, never in libbvg_b200.so): every activation / convolution launch runs a
-// second time into a scratch buffer on the same stream and a compare kernel counts the words that differ - a kernel whose
-// result depends on what else is resident on its SMs shows up as a non-zero counter of ITS launch record (tools/soak_dual.py).
-struct DualLog { long long idx; float a, b; float r[7]; int tag; int pad; };
-__device__ DualLog g_dual_log[256];
-__device__ unsigned int g_dual_nlog;
-__global__ void dual_cmp_kernel(const uint32_t* a, const uint32_t* b, long long n, unsigned int* slot, const float* res,
-                                long long blk, int tag) {
-  unsigned int d = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (a[i] != b[i]) {
-      ++d;
-      const unsigned int k = atomicAdd(&g_dual_nlog, 1u);
-      if (k < 256) {
-        DualLog e;
-        e.idx = i; e.a = __uint_as_float(a[i]); e.b = __uint_as_float(b[i]); e.tag = tag; e.pad = 0;
-        for (int q = 0; q < 7; ++q) {
-          const long long j = i + (long long)(q - 3) * blk;
-          e.r[q] = (res && j >= 0 && j < n) ? res[j] : 0.f;
-        }
-        g_dual_log[k] = e;
-      }
-    }
-  }
-  if (d) atomicAdd(slot, d);
-}
-static unsigned int* g_dual = nullptr;
-static int g_dual_n = 0;
-static int g_dual_tags[8192];
-static void* g_dual_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-static cudaStream_t g_dual_streams[4] = {nullptr, nullptr, nullptr, nullptr};
-static const size_t kDualBytes = (size_t)96 << 20;
-static void* dual_scratch(cudaStream_t st, size_t bytes) {
-  if (bytes > kDualBytes) return nullptr;
-  for (int i = 0; i < 4; ++i) {
-    if (g_dual_scratch[i] && g_dual_streams[i] == st) return g_dual_scratch[i];
-    if (!g_dual_scratch[i]) {
-      if (cudaMalloc(&g_dual_scratch[i], kDualBytes) != cudaSuccess) return nullptr;
-      g_dual_streams[i] = st;
-      return g_dual_scratch[i];
-    }
-  }
-  return nullptr;
-}
-static void dual_check(cudaStream_t st, const void* a, const void* b, size_t bytes, int tag, const float* res = nullptr,
-                       long long blk = 0) {
-  if (!g_dual || g_dual_n >= 8192) return;
-  g_dual_tags[g_dual_n] = tag;
-  dual_cmp_kernel<<<148, 256, 0, st>>>((const uint32_t*)a, (const uint32_t*)b, (long long)(bytes / 4), g_dual + g_dual_n, res, blk, tag);
-  ++g_dual_n;
-}
-extern "C" int bvg_dual_log(void* out, int max) {
-  cudaDeviceSynchronize();
-  unsigned int n = 0;
-  cudaMemcpyFromSymbol(&n, g_dual_nlog, sizeof(n));
-  if (n > 256) n = 256;
-  if ((int)n > max) n = max;
-  cudaMemcpyFromSymbol(out, g_dual_log, n * sizeof(DualLog));
-  unsigned int z = 0;
-  cudaMemcpyToSymbol(g_dual_nlog, &z, sizeof(z));
-  return (int)n;
-}
-extern "C" int bvg_dual_begin() {
-  if (!g_dual) cudaMalloc((void**)&g_dual, 8192 * sizeof(unsigned int));
-  cudaDeviceSynchronize();
-  cudaMemset(g_dual, 0, 8192 * sizeof(unsigned int));
-  g_dual_n = 0;
-  return 0;
-}
-extern "C" int bvg_dual_read(unsigned int* counts, int* tags, int max) {
-  cudaDeviceSynchronize();
-  const int n = g_dual_n < max ? g_dual_n : max;
-  cudaMemcpy(counts, g_dual, n * sizeof(unsigned int), cudaMemcpyDeviceToHost);
-  for (int i = 0; i < n; ++i) tags[i] = g_dual_tags[i];
-  return n;
-}
-#endif
 
-#ifdef BVG_TRACE
-// Debug builds only (BVG_EXTRA_FLAGS=-DBVG_TRACE, never in libbvg_b200.so): a position-weighted checksum of every tensor a
-// forward writes, taken on the writing stream right behind the kernel, to find the first launch whose result differs
-// between two schedules (tools/soak_trace.py).
-__global__ void trace_sum_kernel(const uint32_t* p, long long n, unsigned long long* slot) {
-  unsigned long long s = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    s += (unsigned long long)p[i] * (unsigned long long)((i % 8191) + 1);
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(slot, s);
-}
-static unsigned long long* g_trace = nullptr;
-static int g_trace_n = 0;
-static int g_trace_tags[8192];
-static void trace_out(cudaStream_t st, const void* p, size_t bytes, int tag) {
-  if (!g_trace || g_trace_n >= 8192) return;
-  g_trace_tags[g_trace_n] = tag;
-  trace_sum_kernel<<<296, 256, 0, st>>>((const uint32_t*)p, (long long)(bytes / 4), g_trace + g_trace_n);
-  ++g_trace_n;
-}
-extern "C" int bvg_trace_begin() {
-  if (!g_trace) cudaMalloc((void**)&g_trace, 8192 * sizeof(unsigned long long));
-  cudaDeviceSynchronize();
-  cudaMemset(g_trace, 0, 8192 * sizeof(unsigned long long));
-  g_trace_n = 0;
-  return 0;
-}
-extern "C" int bvg_trace_read(unsigned long long* sums, int* tags, int max) {
-  cudaDeviceSynchronize();
-  const int n = g_trace_n < max ? g_trace_n : max;
-  cudaMemcpy(sums, g_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  for (int i = 0; i < n; ++i) tags[i] = g_trace_tags[i];
-  return n;
-}
-#define BVG_TRACE_OUT(st, p, bytes, tag) trace_out(st, p, bytes, tag)
-#else
-#define BVG_TRACE_OUT(st, p, bytes, tag)
-#endif
 
 static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, void* out, int out_dt,
                     const float* res, const float* accum, float scale, int B, int64_t T, cudaStream_t st,
@@ -455,23 +339,6 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
   ProfScope ps(v, st, umma ? CAT_CONV_UMMA : CAT_CONV_SIMT, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   ps.cin = c.Cin; ps.cout = c.up > 0 ? -c.Cout : c.Cout; ps.k = c.k_torch; ps.dil = c.dil; ps.rows = (long long)B * T;
   const int rc_ = umma ? conv_umma_launch(a, 0, st) : conv_simt_launch(a, st);
-#ifdef BVG_DUAL
-  if (!rc_ && umma && out != (const void*)res && out != (const void*)accum) {
-    const size_t nb_ = (size_t)B * T * c.Cout_n * dtype_size(out_dt);
-    void* sc_ = dual_scratch(st, nb_);
-    if (sc_) {
-      ConvArgs a2_ = a;
-      a2_.out = sc_;
-      conv_umma_launch(a2_, 0, st);
-      {
-        const int rep_ = c.Cout_n <= 32 ? 4 : (c.Cout_n <= 64 ? 2 : 1);
-        dual_check(st, out, sc_, nb_, 1000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil, out_dt == BVG_F32 ? res : nullptr,
-                   (long long)(accum ? 16 : 32) * rep_ * c.Cout_n);
-      }
-    }
-  }
-#endif
-  BVG_TRACE_OUT(st, out, (size_t)B * T * c.Cout_n * dtype_size(out_dt), 1000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
   return rc_;
 }
 
@@ -500,19 +367,6 @@ static int run_conv_act(bvg_vocoder* v, const ConvW& c, const ActW& act, const v
   ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   ps.cin = c.Cin; ps.cout = c.Cout; ps.k = c.k_torch; ps.dil = 100 + c.dil; ps.rows = (long long)B * T;
   const int rc_ = conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st);
-#ifdef BVG_DUAL
-  if (!rc_) {
-    const size_t nb_ = (size_t)B * T * c.Cout_n * 2;
-    void* sc_ = dual_scratch(st, nb_);
-    if (sc_) {
-      ConvArgs a2_ = a;
-      a2_.out = sc_;
-      conv_act_fused_launch(a2_, act.alpha, act.beta, act.taps, st);
-      dual_check(st, out, sc_, nb_, 2000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
-    }
-  }
-#endif
-  BVG_TRACE_OUT(st, out, (size_t)B * T * c.Cout_n * 2, 2000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
   return rc_;
 }
 
@@ -542,8 +396,6 @@ static int run_conv_res_act(bvg_vocoder* v, const ConvW& c, const ActW& act, con
   ProfScope ps(v, st, CAT_CONV_UMMA, 2.0 * c.Cout * c.Cin * c.k_torch * (double)T * B);
   ps.cin = c.Cin; ps.cout = c.Cout; ps.k = c.k_torch; ps.dil = 200 + c.dil; ps.rows = (long long)B * T;
   const int rc_ = conv_act_fused_launch(a, act.alpha, act.beta, act.taps, st, y_out);
-  BVG_TRACE_OUT(st, a_out, (size_t)B * T * c.Cout_n * 2, 3000000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
-  BVG_TRACE_OUT(st, y_out, (size_t)B * T * c.Cout_n * 4, 3500000 + c.Cin * 1000 + c.k_torch * 10 + c.dil);
   return rc_;
 }
 
@@ -558,18 +410,6 @@ static int run_act(bvg_vocoder* v, const ActW& a, const void* in, int in_dt, voi
   // next conv need (a stale NaN bit pattern times 0 would poison the accumulator).  Saves a quarter of that stage's work.
   const int Cact = (a.Cp == a.C + 8 && !(a.C & 1) && T >= 64) ? a.C : a.Cp;   // (short sequences: all-scalar launch, all channels)
   const int rc_ = act1d_cl_launch(out, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
-#ifdef BVG_DUAL
-  if (!rc_) {
-    const size_t nb_ = (size_t)B * T * a.Cp * dtype_size(out_dt);
-    void* sc_ = dual_scratch(st, nb_);
-    if (sc_) {
-      cudaMemcpyAsync(sc_, out, nb_, cudaMemcpyDeviceToDevice, st);   // pad channels the kernel does not write
-      act1d_cl_launch(sc_, in, a.alpha, a.beta, a.taps, B, T, Cact, in_dt, out_dt, fast, st, a.Cp);
-      dual_check(st, out, sc_, nb_, 4000000 + a.C * 1000 + (int)dtype_size(in_dt));
-    }
-  }
-#endif
-  BVG_TRACE_OUT(st, out, (size_t)B * T * a.Cp * dtype_size(out_dt), 4000000 + a.C * 1000 + (int)dtype_size(in_dt));
   return rc_;
 }
 
