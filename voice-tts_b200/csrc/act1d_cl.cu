@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(128)
 act1d_cl_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, const float* __restrict__ alpha_log,
                 const float* __restrict__ beta_log, const Taps taps, int B, int64_t T, int C, int ld, int L,
                 int nseg, int nseg_head, int64_t tail_start, int64_t nitems) {
+  pdl_launch_dependents();
+  pdl_wait();
   act1d_cl_body<Tin, Tout, VEC, FAST>(dst, src, alpha_log, beta_log, taps, B, T, C, ld, L, nseg, nseg_head, tail_start, nitems,
                                       (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
@@ -304,6 +306,8 @@ act1d_cl_packed_kernel(Tout* __restrict__ dst, const Tin* __restrict__ src, cons
                        const float* __restrict__ beta_log, const TapsPacked tp, int B, int64_t T, int C, int ld, int L,
                        int nseg_int, int head_len, int64_t nitems, const Taps taps, int main_blocks, int nseg_edge,
                        int nseg_head, int64_t tail_start, int64_t nitems_edge) {
+  pdl_launch_dependents();
+  pdl_wait();
   if ((int)blockIdx.x >= main_blocks) {
     // the last blocks of the grid take the sequence ends (short segments, scalar edge-aware path): they run
     // beside the interior blocks instead of as a separate ~10 us launch behind them
@@ -381,7 +385,7 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
     const int64_t nitems = (int64_t)B * nseg * C;
     const int64_t blocks = ceil_div(nitems, threads);
     if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
-    act1d_cl_kernel<Tin, Tout, 1, FAST><<<(unsigned)blocks, threads, 0, st>>>(
+    launch_pdl(act1d_cl_kernel<Tin, Tout, 1, FAST>, (unsigned)blocks, threads, 0, st,
         (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, ld, L, nseg, nseg, T, nitems);
     BVG_LAUNCHED();
     return BVG_OK;
@@ -414,11 +418,11 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
     const int64_t blocks = main_blocks + ceil_div(nitems_edge, kPackedThreads);
     if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
     if (ld > C)
-      act1d_cl_packed_kernel<Tin, Tout, FAST, true><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
+      launch_pdl(act1d_cl_packed_kernel<Tin, Tout, FAST, true>, (unsigned)blocks, kPackedThreads, 0, st,
           (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, ld, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
           nseg, nseg_head, tail_start, nitems_edge);
     else
-      act1d_cl_packed_kernel<Tin, Tout, FAST, false><<<(unsigned)blocks, kPackedThreads, 0, st>>>(
+      launch_pdl(act1d_cl_packed_kernel<Tin, Tout, FAST, false>, (unsigned)blocks, kPackedThreads, 0, st,
           (Tout*)dst, (const Tin*)src, alpha_log, beta_log, tp, B, T, C, ld, L, (int)n_int, kEdge, nitems, taps, (int)main_blocks,
           nseg, nseg_head, tail_start, nitems_edge);
     BVG_LAUNCHED();
@@ -427,7 +431,7 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
   if (ld > C) BVG_FAIL(BVG_EINVAL, "act1d_cl: a row pitch wider than the channel count needs T >= 49");
   const int64_t blocks = ceil_div(nitems_edge, threads);
   if (blocks > 0x7fffffffLL) BVG_FAIL(BVG_EINVAL, "act1d_cl: tensor too large (%lld blocks)", (long long)blocks);
-  act1d_cl_kernel<Tin, Tout, 2, FAST><<<(unsigned)blocks, threads, 0, st>>>(
+  launch_pdl(act1d_cl_kernel<Tin, Tout, 2, FAST>, (unsigned)blocks, threads, 0, st,
       (Tout*)dst, (const Tin*)src, alpha_log, beta_log, taps, B, T, C, ld, kEdge, nseg, nseg_head, T, nitems_edge);
   BVG_LAUNCHED();
   return BVG_OK;

@@ -10,6 +10,7 @@ namespace bvg {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+thread_local int g_pdl = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <utility>
 
 #include "../../include/bvg_b200.h"
 
@@ -70,6 +71,37 @@ struct DeviceGuard {
   ::bvg::DeviceGuard _dg(dev);                                                   \
   if (!_dg.ok) BVG_FAIL(BVG_ENODEV, "cannot make device %d current", (int)(dev))
 
+// ------------------------------------------------ programmatic dependent launch (PDL) ----
+// Kernels of the bf16 layer sequence are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel
+// of a stream may become resident (where there is room) and run its prologue - mbarrier init, tensor-map prefetch, TMEM
+// allocation - while its predecessor drains; it then blocks in `griddepcontrol.wait` (pdl_wait) until the predecessor
+// has COMPLETED and its writes are visible, before it touches global memory.  Every such kernel executes pdl_wait
+// unconditionally, so completion is transitive along a stream (kernel n+1 past its wait => kernel n complete => kernel n
+// was past its own wait => kernel n-1 complete ...), and kernels launched the ordinary way keep full stream order.
+// g_pdl: set per forward by the handle (option "pdl"); thread-local because launches happen on the caller's thread.
+extern thread_local int g_pdl;
+struct PdlScope {
+  int prev;
+  explicit PdlScope(int on) : prev(g_pdl) { g_pdl = on; }
+  ~PdlScope() { g_pdl = prev; }
+};
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface through BVG_LAUNCHED()
+}
+#endif
+
 struct Taps {
   float up[12];    // up-filter taps already multiplied by the x2 gain
   float down[12];
@@ -80,6 +112,10 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // --------------------------------------------------------- device helpers ----
 #ifdef __CUDACC__
+
+// see "programmatic dependent launch" above: first statement of a PDL kernel / last statement before its first global access
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);

@@ -117,6 +117,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t sink_u32 = smem_u32(tmem_slot + 4 + (threadIdx.x / 32));   // one sink word per warp (loads_landed, common.cuh)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < U2_AIN_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -138,6 +139,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above overlapped the predecessor's tail; no global access before this line (common.cuh, PDL)
   const uint32_t tmem_base = *tmem_slot;
   const int CB = p.CB, CW = p.CW;
 
@@ -483,7 +485,7 @@ int conv_umma2_launch(const ConvArgs& a, int variant, cudaStream_t st) {
   do {                                                                                                               \
     static std::atomic<unsigned long long> attr_done_{0};                                                              \
     if (int rc_ = smem_attr_once(conv_umma2_kernel<N, O>, U2_SMEM_BYTES, attr_done_)) return rc_;                      \
-    conv_umma2_kernel<N, O><<<grid, U2_THREADS, smem, st>>>(mx, mw, mo, mr, ma, p);                         \
+    launch_pdl(conv_umma2_kernel<N, O>, grid, U2_THREADS, smem, st, mx, mw, mo, mr, ma, p);                            \
   } while (0)
   const bool ob = a.out_dtype == BVG_BF16;
   if (nin == 0) { if (ob) BVG_U2_LAUNCH(0, true); else BVG_U2_LAUNCH(0, false); }

@@ -315,6 +315,7 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < UA_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -333,6 +334,7 @@ conv_umma2a_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // no global access above this line (common.cuh, PDL)
   const uint32_t tmem_base = *tmem_slot;
   const int CW = p.CW;
 
@@ -573,11 +575,11 @@ int conv_umma2a_launch(const ConvArgs& a, const float* alpha_log, const float* b
   if (a.res) {
     static std::atomic<unsigned long long> attr_done_res{0};
     if (int rc_ = smem_attr_once(conv_umma2a_kernel<true>, UA_SMEM_BYTES, attr_done_res)) return rc_;
-    conv_umma2a_kernel<true><<<grid, UA_THREADS, smem, st>>>(mx, mw, mo, mt, p);
+    launch_pdl(conv_umma2a_kernel<true>, grid, UA_THREADS, smem, st, mx, mw, mo, mt, p);
   } else {
     static std::atomic<unsigned long long> attr_done_plain{0};
     if (int rc_ = smem_attr_once(conv_umma2a_kernel<false>, UA_SMEM_BYTES, attr_done_plain)) return rc_;
-    conv_umma2a_kernel<false><<<grid, UA_THREADS, smem, st>>>(mx, mw, mo, mt, p);
+    launch_pdl(conv_umma2a_kernel<false>, grid, UA_THREADS, smem, st, mx, mw, mo, mt, p);
   }
   BVG_LAUNCHED();
   return BVG_OK;

@@ -82,6 +82,8 @@ struct bvg_vocoder {
   int fuse_res_min_kc = 4096;      // smallest k * Cin whose conv2 takes the fused residual + activation epilogue
   int opt_fuse_unit = 0;           // 1: whole AMP units of <= 96-channel stages as one kernel (amp_unit.cu; bf16 mode) - measured slower
                                    // than the layer-by-layer path on B200, so off by default
+  int opt_pdl = 0;                 // programmatic dependent launch of the conv / activation kernels (common.cuh): bit-identical,
+                                   // measured no gain (16 x 10 s: 39.8 vs 39.6 ms; 1 x 2 s: 1.44 vs 1.35 ms) - off by default
   int opt_streams = 3;             // AMP blocks of one stage run on up to this many streams (1 = serial); see DESIGN.md 8.5
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // internal streams for AMP blocks 0 .. nk-2
   cudaEvent_t ev_fork = nullptr, ev_blk[3] = {nullptr, nullptr, nullptr};
@@ -647,6 +649,7 @@ int vocoder_forward(bvg_vocoder* v, const float* mel, const float* emb, void* wa
   int rc = ensure_device_ok();
   if (rc) return rc;
   const uint64_t l0 = g_launches.load();
+  PdlScope pdl_scope(v->opt_pdl && !v->opt_profile);   // per-launch profiling events want plain stream order
   prof_break(v);   // the caller may have enqueued work on `st` since the last forward
   const int mb = max_microbatch(v, B, T0);
   rc = ensure_arena(v, plan_buffers(v, mb, T0, nullptr));
@@ -1067,6 +1070,7 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
       {"fuse_res", &v->opt_fuse_res, true},     {"fuse_res_min_kc", &v->fuse_res_min_kc, true},
       {"fuse_act", &v->opt_fuse_act, true},     {"fuse_unit", &v->opt_fuse_unit, true},
       {"streams", &v->opt_streams, true},       {"conv_own_sm", &v->opt_own_sm, true},
+      {"pdl", &v->opt_pdl, true},
   };
   for (const Opt& o : opts) {
     if (strcmp(key, o.name)) continue;
