@@ -204,10 +204,11 @@ int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
  * "fast_sin" (0/1), "workspace_mb" (micro-batching cap), "profile" (0/1: one CUDA-event pair per launch, read back with
  * bvg_profile_read), "fuse_act" (0 off, 1 measured policy, 2 always: conv1 + following activation in one kernel),
  * "fuse_res" / "fuse_res_min_kc" (conv2 + residual + next activation in one kernel: 0 off, 1 when k*Cin >= min_kc,
- * 2 always), "fuse_unit" (1 [default]: whole AMP units of <= 96-channel stages as ONE kernel, bvg_amp_unit_fwd; 0: layer by
+ * 2 always), "fuse_unit" (1: whole AMP units of <= 96-channel stages as ONE kernel, bvg_amp_unit_fwd; 0 [default, faster]: layer by
  * layer), "streams" (3 [default]: the AMP blocks of a stage on separate internal streams that fork from and join the caller's
  * stream; 1: serial; the result is bit-identical either way), "conv_own_sm" (1 [default]: the persistent tcgen05 conv kernels request the whole shared-memory carve-out of their SM;
- * 0: they leave room for one shared-memory-free block of another stream beside them).  Options that change what a forward enqueues drop captured graphs. */
+ * 0: they leave room for one shared-memory-free block of another stream beside them), "pdl" (1: programmatic dependent launch of the
+ * conv / activation kernels; 0 [default]: measured no gain).  Options that change what a forward enqueues drop captured graphs. */
 int bvg_set_option(bvg_vocoder* v, const char* key, int value);
 /* per-kernel CUDA-event timing (set option "profile"=1 first; disables graph replay while on):
  * category 0 = tcgen05 conv, 1 = SIMT conv, 2 = fused activation, 3 = other, 4 = whole AMP unit in one kernel
@@ -219,6 +220,49 @@ int bvg_profile_read(bvg_vocoder* v, int category, double* ms, double* work, int
 int bvg_profile_dump(bvg_vocoder* v, const char* path);
 /* introspection for benchmarks: kernels launched by the last forward */
 int bvg_last_forward_launches(const bvg_vocoder* v);
+
+/* ------------------------------------------------------------------------
+ * The s2mel tail in front of the vocoder: what DiT.forward does after its transformer
+ * (indextts/s2mel/modules/diffusion_transformer.py:245-256) - conv1 -> WN (indextts/s2mel/modules/wavenet.py:103-164, reflect-padded
+ * SConv1d in_layers, gated tanh * sigmoid, res / skip 1x1 convs, x_mask) conditioned on t_embedder2(t) -> + res_projection(x_res)
+ * -> FinalLayer (LayerNorm, adaLN modulate from t1, Linear) -> conv2 - and one Euler / classifier-free-guidance update of
+ * BASECFM.solve_euler (indextts/s2mel/modules/flow_matching.py:85-113).  Same build protocol as the vocoder handle:
+ * create -> set_tensor (folded weights, reference state-dict names relative to the DiT module: "conv1.weight",
+ * "t_embedder2.mlp.0.weight", "t_embedder2.freqs", "wavenet.cond_layer.weight", "wavenet.in_layers.3.bias",
+ * "wavenet.res_skip_layers.7.weight", "res_projection.bias", "final_layer.adaLN_modulation.1.weight",
+ * "final_layer.linear.weight", "conv2.bias", ... ) -> finalize -> forward calls.
+ */
+typedef struct bvg_s2mel_config {
+  int hidden;        /* wavenet.hidden_dim (512) */
+  int dit_hidden;    /* DiT.hidden_dim (512): width of x_res.  t1 = DiT.t_embedder(t) feeds FinalLayer(wavenet.hidden_dim), so the
+                        reference itself needs dit_hidden == hidden whenever the wavenet head is used */
+  int n_layers;      /* wavenet.num_layers (8) */
+  int kernel_size;   /* wavenet.kernel_size (5), odd */
+  int dilation_rate; /* wavenet.dilation_rate: 1 (the only value built) */
+  int out_channels;  /* DiT.in_channels (80 mel bins) */
+  int freq_dim;      /* TimestepEmbedder.frequency_embedding_size (256) */
+  int mode;          /* BVG_MODE_* */
+  int device;
+} bvg_s2mel_config;
+typedef struct bvg_s2mel_tail bvg_s2mel_tail;
+
+int bvg_s2mel_tail_create(const bvg_s2mel_config* cfg, bvg_s2mel_tail** out);
+void bvg_s2mel_tail_destroy(bvg_s2mel_tail* h);
+int bvg_s2mel_tail_set_tensor(bvg_s2mel_tail* h, const char* name, const float* data, int64_t numel, int is_device);
+int bvg_s2mel_tail_finalize(bvg_s2mel_tail* h);
+int64_t bvg_s2mel_tail_workspace_bytes(const bvg_s2mel_tail* h, int B, int T);
+/* x_res [B, T, dit_hidden] fp32 (the transformer output after skip_linear, diffusion_transformer.py:243-244),
+ * x_lens [B] int32 or NULL (x_mask = t < x_lens[b]; NULL: all frames valid), t [B] fp32 (the solver's time),
+ * t1 [B, hidden] fp32 (DiT.t_embedder(t), computed by the caller for the transformer anyway) -> out [B, out_channels, T] fp32.
+ * All device pointers; T > (kernel_size - 1) / 2. */
+int bvg_s2mel_tail_fwd(bvg_s2mel_tail* h, const float* x_res, const int* x_lens, const float* t, const float* t1, float* out,
+                       int B, int T, bvg_stream_t stream);
+/* One Euler step of BASECFM.solve_euler in place on x [B, C, T] fp32 (device):
+ *   cfg_rate > 0: dphi is the stacked estimator output [2B, C, T]; d = (1 + cfg_rate) * dphi[:B] - cfg_rate * dphi[B:]
+ *   else        : dphi is [B, C, T]; d = dphi
+ *   x = x + dt * d;  x[:, :, :prompt_len] = 0            (flow_matching.py:103-112; bit-identical to the fp32 tensor ops) */
+int bvg_cfm_euler_step(float* x, const float* dphi, float dt, double cfg_rate, int B, int C, int64_t T, int64_t prompt_len,
+                       bvg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -216,6 +216,96 @@ def v1_attr(h):
     return H(dict(h))
 
 
+S2MEL_CASES = [
+    # name, config overrides, B, T, x_lens (None: all frames valid), seed
+    ("full", {}, 2, 61, None, 11),
+    ("ragged", {"hidden": 64, "dit_hidden": 64, "n_layers": 3}, 3, 37, [37, 20, 5], 12),
+    ("k3", {"hidden": 32, "dit_hidden": 32, "n_layers": 2, "kernel_size": 3}, 1, 9, None, 13),
+    ("k7", {"hidden": 48, "dit_hidden": 48, "n_layers": 2, "kernel_size": 7, "out_channels": 20}, 2, 130, [130, 77], 14),
+]
+
+
+def s2mel_args(cfg):
+    """the `args` namespace DiT / BASECFM read (diffusion_transformer.py:105-175, flow_matching.py:10-29)"""
+    from types import SimpleNamespace as NS
+    return NS(DiT=NS(hidden_dim=cfg["dit_hidden"], num_heads=2, depth=1, in_channels=cfg["out_channels"], content_type="discrete",
+                     content_codebook_size=16, content_dim=cfg["dit_hidden"], is_causal=False, final_layer_type="wavenet",
+                     style_condition=True, class_dropout_prob=0.1, long_skip_connection=True, time_as_token=False,
+                     style_as_token=False, uvit_skip_connection=True, block_size=8192, zero_prompt_speech_token=False),
+              wavenet=NS(hidden_dim=cfg["hidden"], kernel_size=cfg["kernel_size"], dilation_rate=cfg["dilation_rate"],
+                         num_layers=cfg["n_layers"], p_dropout=0.2, style_condition=True),
+              style_encoder=NS(dim=24), reg_loss_type="l1", dit_type="DiT")
+
+
+def gen_s2mel():
+    """Tail goldens through the UNMODIFIED reference: DiT.forward runs end to end; forward hooks capture the tail's inputs
+    (x_res = output of skip_linear, t1 = output of t_embedder); its return value is the tail's output.  The tail weights
+    are the deterministic synthetic ones of synth.make_s2mel_tail_state_dict, loaded through the host mirror's key mapping."""
+    import types
+    if "munch" not in sys.modules:                       # commons.py imports munch (absent here) for an unrelated helper
+        sys.modules["munch"] = types.ModuleType("munch")
+        sys.modules["munch"].Munch = dict
+    refshim.load()
+    from indextts.s2mel.modules import diffusion_transformer, flow_matching
+    tail_mod = importlib.import_module("voice-tts_b200.s2mel_tail")
+    from oracle import s2mel_oracle
+    out = {}
+    for name, over, B, T, lens, seed in S2MEL_CASES:
+        cfg = config.s2mel_tail_config(**over)
+        torch.manual_seed(seed)
+        dit = diffusion_transformer.DiT(s2mel_args(cfg)).eval()
+        sd = synth.make_s2mel_tail_state_dict(cfg, seed=4321 + seed)
+        mirror = tail_mod.S2MelTail(cfg, precision="fp32")
+        mirror.load_folded_state_dict(sd)
+        res = dit.load_state_dict(mirror.state_dict(), strict=False)     # reference key names incl. weight_g / weight_v
+        assert not res.unexpected_keys, res.unexpected_keys
+        assert not [k for k in res.missing_keys if k.startswith(tail_mod.TAIL_PREFIXES)], res.missing_keys
+        dit.setup_caches(B, T)
+        cap = {}
+        dit.skip_linear.register_forward_hook(lambda m, i, o: cap.__setitem__("x_res", o.detach().clone()))
+        dit.t_embedder.register_forward_hook(lambda m, i, o: cap.__setitem__("t1", o.detach().clone()))
+        g = torch.Generator().manual_seed(seed)
+        C = cfg["out_channels"]
+        x = torch.randn(B, C, T, generator=g)
+        prompt_x = torch.randn(B, C, T, generator=g) * 0.5
+        x_lens = torch.tensor(lens if lens is not None else [T] * B)
+        t = torch.rand(B, generator=g)
+        style = torch.randn(B, 24, generator=g)
+        cond = torch.randn(B, T, cfg["dit_hidden"], generator=g)
+        with torch.no_grad():
+            y = dit(x, prompt_x, x_lens, t, style, cond)
+        # scale x_res up to O(1) entries? no - keep exactly what the reference's transformer produced
+        for k, v in (("x_res", cap["x_res"]), ("t1", cap["t1"]), ("t", t), ("x_lens", x_lens.int()), ("out", y)):
+            out["%s.%s" % (name, k)] = v.numpy()
+        out[name + ".seed"] = np.array([4321 + seed])
+        out[name + ".cfg"] = np.array([cfg[k] for k in ("hidden", "dit_hidden", "n_layers", "kernel_size", "dilation_rate",
+                                                        "out_channels", "freq_dim")])
+        ours = s2mel_oracle.tail_forward(sd, cfg, cap["x_res"], x_lens if lens is not None else None, t, cap["t1"])
+        print(name, tuple(cap["x_res"].shape), "->", tuple(y.shape), "absmax %.4f" % y.abs().max(),
+              "oracle max|diff| %.3g" % (ours - y).abs().max())
+    # the solver: BASECFM.solve_euler around a toy estimator (exact fp32 arithmetic), with and without CFG
+    for name, B, C, T, plen, steps, rate, seed in (("euler_cfg", 2, 80, 50, 17, 25, 0.7, 21), ("euler_nocfg", 1, 20, 33, 0, 6, 0.0, 22),
+                                                   ("euler_cfg2", 3, 16, 19, 19, 10, 0.5, 23)):
+        cfm = flow_matching.BASECFM(s2mel_args(config.s2mel_tail_config()))
+        cfm.estimator = s2mel_oracle.toy_estimator
+        g = torch.Generator().manual_seed(seed)
+        z = torch.randn(B, C, T, generator=g)
+        prompt = torch.randn(B, C, plen, generator=g)
+        mu = torch.randn(B, T, 96, generator=g)
+        style = torch.randn(B, 8, generator=g)
+        t_span = torch.linspace(0, 1, steps + 1)
+        import contextlib, io
+        with torch.no_grad(), contextlib.redirect_stderr(io.StringIO()):
+            y = cfm.solve_euler(z.clone(), torch.tensor([T] * B), prompt, mu.clone(), style, None, t_span, inference_cfg_rate=rate)
+        ours = s2mel_oracle.solve_euler(s2mel_oracle.toy_estimator, z.clone(), torch.tensor([T] * B), prompt, mu.clone(), style, t_span, rate)
+        for k, v in (("z", z), ("prompt", prompt), ("mu", mu), ("style", style), ("out", y)):
+            out["%s.%s" % (name, k)] = v.numpy()
+        out[name + ".meta"] = np.array([steps, rate])
+        print(name, tuple(z.shape), "steps", steps, "cfg", rate, "absmax %.4f" % y.abs().max(), "oracle bit-identical:",
+              bool(torch.equal(ours, y)))
+    np.savez_compressed(os.path.join(OUT, "s2mel_tail.npz"), **out)
+
+
 def main():
     assert refshim.available(), "reference tree not found"
     torch.set_num_threads(os.cpu_count())
@@ -230,6 +320,8 @@ def main():
         gen_headline(mod)
     if not only or "v1" in only:
         gen_v1()
+    if not only or "s2mel" in only:
+        gen_s2mel()
 
 
 if __name__ == "__main__":

@@ -192,3 +192,55 @@ def test_conv_transpose_3tap_polyphase_general(k, u):
     ref = O.conv_transpose1d(x, w, b, u)
     assert ref.shape[-1] == 9 * u
     assert (O.conv_transpose1d_taps(x, w, b, u) - ref).abs().max() < 1e-12
+
+
+# ---- s2mel tail ----------------------------------------------------------------------
+S2MEL_CFG_KEYS = ("hidden", "dit_hidden", "n_layers", "kernel_size", "dilation_rate", "out_channels", "freq_dim")
+
+
+@pytest.mark.parametrize("name", ("full", "ragged", "k3", "k7"))
+def test_s2mel_tail_oracle_matches_reference_goldens(golden, synth, name):
+    """the oracle restatement against the unmodified reference DiT.forward (goldens of oracle/make_golden.py s2mel)"""
+    from oracle import s2mel_oracle as S
+    g = golden("s2mel_tail")
+    c = dict(zip(S2MEL_CFG_KEYS, (int(v) for v in g[name + ".cfg"])))
+    sd = synth.make_s2mel_tail_state_dict(c, seed=int(g[name + ".seed"][0]))
+    tt = lambda k: torch.from_numpy(g["%s.%s" % (name, k)])
+    ref = tt("out")
+    y = S.tail_forward(sd, c, tt("x_res"), tt("x_lens"), tt("t"), tt("t1"))
+    assert float((y - ref).abs().max() / ref.abs().max()) <= 1e-5
+    y64 = S.tail_forward(sd, c, tt("x_res"), tt("x_lens"), tt("t"), tt("t1"), dtype=torch.float64)
+    assert float((y64.float() - ref).abs().max() / ref.abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ("euler_cfg", "euler_nocfg", "euler_cfg2"))
+def test_s2mel_euler_oracle_bit_exact_vs_reference_goldens(golden, name):
+    from oracle import s2mel_oracle as S
+    g = golden("s2mel_tail")
+    z, prompt, mu, style, ref = (torch.from_numpy(g["%s.%s" % (name, k)]) for k in ("z", "prompt", "mu", "style", "out"))
+    steps, rate = int(g[name + ".meta"][0]), float(g[name + ".meta"][1])
+    B, _, T = z.shape
+    y = S.solve_euler(S.toy_estimator, z, torch.tensor([T] * B), prompt, mu, style, torch.linspace(0, 1, steps + 1), rate)
+    assert torch.equal(y, ref)
+
+
+def test_s2mel_tail_host_mirror_key_names(synth, cfg):
+    """the host mirror exposes the reference's DiT key names for the tail (diffusion_transformer.py:139-157, wavenet.py:119-138,
+    encodec.py:124-138,206-208) and its folded / unfolded mappings round-trip"""
+    import importlib
+    tm = importlib.import_module("voice-tts_b200.s2mel_tail")
+    c = cfg.s2mel_tail_config(hidden=32, dit_hidden=32, n_layers=2)
+    m = tm.S2MelTail(c, precision="fp32")
+    keys = set(m.state_dict().keys())
+    for k in ("conv1.weight", "conv1.bias", "t_embedder2.mlp.0.weight", "t_embedder2.mlp.2.bias", "t_embedder2.freqs",
+              "wavenet.cond_layer.conv.conv.weight_g", "wavenet.cond_layer.conv.conv.weight_v", "wavenet.cond_layer.conv.conv.bias",
+              "wavenet.in_layers.1.conv.conv.weight_v", "wavenet.res_skip_layers.0.conv.conv.bias", "res_projection.weight",
+              "final_layer.linear.weight_g", "final_layer.linear.weight_v", "final_layer.adaLN_modulation.1.weight", "conv2.weight"):
+        assert k in keys, k
+    assert all(k.startswith(tm.TAIL_PREFIXES) for k in keys)
+    sd = synth.make_s2mel_tail_state_dict(c, seed=3)
+    m.load_folded_state_dict(sd)
+    back = m.folded_state_dict()
+    assert set(back) == set(sd)
+    for k in sd:
+        assert torch.allclose(back[k], sd[k], rtol=1e-6, atol=1e-7), k

@@ -29,6 +29,12 @@ class BvgConfig(ctypes.Structure):
     ]
 
 
+class S2MelConfig(ctypes.Structure):
+    _fields_ = [("hidden", ctypes.c_int), ("dit_hidden", ctypes.c_int), ("n_layers", ctypes.c_int),
+                ("kernel_size", ctypes.c_int), ("dilation_rate", ctypes.c_int), ("out_channels", ctypes.c_int),
+                ("freq_dim", ctypes.c_int), ("mode", ctypes.c_int), ("device", ctypes.c_int)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/bvg_b200.h declares
@@ -59,6 +65,13 @@ SYMBOLS = {
     "bvg_profile_dump": (_i, [_vp, ctypes.c_char_p]),
     "bvg_profile_read": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                               ctypes.POINTER(ctypes.c_int)]),
+    "bvg_s2mel_tail_create": (_i, [ctypes.POINTER(S2MelConfig), ctypes.POINTER(_vp)]),
+    "bvg_s2mel_tail_destroy": (None, [_vp]),
+    "bvg_s2mel_tail_set_tensor": (_i, [_vp, ctypes.c_char_p, _vp, _i64, _i]),
+    "bvg_s2mel_tail_finalize": (_i, [_vp]),
+    "bvg_s2mel_tail_workspace_bytes": (_i64, [_vp, _i, _i]),
+    "bvg_s2mel_tail_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "bvg_cfm_euler_step": (_i, [_vp, _vp, _f, ctypes.c_double, _i, _i, _i64, _i64, _vp]),
 }
 
 

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, os.environ.get("BVG_LIB_NAME", "libbvg_b200.so"))   # BVG_LIB_NAME / BVG_EXTRA_FLAGS: debug builds
-SOURCES = ["api.cu", "act1d_cl.cu", "act1d_bct.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_t.cu", "conv_umma2.cu", "conv_umma2a.cu", "amp_unit.cu", "vocoder.cu"]
+SOURCES = ["api.cu", "s2mel_tail.cu", "act1d_cl.cu", "act1d_bct.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_t.cu", "conv_umma2.cu", "conv_umma2a.cu", "amp_unit.cu", "vocoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

@@ -58,6 +58,18 @@ class AttrDict(dict):
         self.__dict__ = self
 
 
+# The s2mel tail: `s2mel.wavenet` / `s2mel.DiT` of the published IndexTTS-2 config.yaml
+# (the reference tree does not ship checkpoints/config.yaml; values restated from the release - every test is parameterised).
+INDEXTTS2_S2MEL_TAIL = {"hidden": 512, "dit_hidden": 512, "n_layers": 8, "kernel_size": 5, "dilation_rate": 1,
+                        "out_channels": 80, "freq_dim": 256}
+
+
+def s2mel_tail_config(**overrides):
+    c = dict(INDEXTTS2_S2MEL_TAIL)
+    c.update(overrides)
+    return c
+
+
 def load_hparams_from_json(path) -> AttrDict:
     with open(path) as f:
         return AttrDict(json.load(f))

@@ -1,0 +1,566 @@
+// The s2mel tail that feeds the vocoder: the WaveNet head behind the DiT transformer and
+// the Euler / classifier-free-guidance update of the flow-matching solver.
+//
+// reference (paths relative to the reference root):
+//   indextts/s2mel/modules/diffusion_transformer.py:245-256   x = conv1(x_res); x = wavenet(x^T, x_mask, g = t_embedder2(t))^T
+//                                                             + res_projection(x_res); x = final_layer(x, t1)^T; x = conv2(x)
+//   indextts/s2mel/modules/diffusion_transformer.py:20-57     TimestepEmbedder (scale 1000, [cos | sin], Linear-SiLU-Linear)
+//   indextts/s2mel/modules/diffusion_transformer.py:82-99     FinalLayer: LayerNorm(eps 1e-6, no affine) -> modulate -> Linear
+//   indextts/s2mel/modules/wavenet.py:103-164                 WN.forward (gated dilated convs, res / skip 1x1 convs, x_mask)
+//   indextts/s2mel/modules/encodec.py:212-228                 SConv1d: reflect padding (k-1)*dil split right = total/2, left = rest
+//   indextts/s2mel/modules/commons.py:133-139                 fused_add_tanh_sigmoid_multiply
+//   indextts/s2mel/modules/flow_matching.py:85-113            solve_euler: CFG combine, x + dt * dphi, prompt frames zeroed
+//
+// Data layout: everything channels-last [B, T, C] like the vocoder (the transformer's output x_res already is).  The dense
+// layers are the vocoder's conv kernels (tcgen05 implicit GEMM in BVG_MODE_BF16, fp32 SIMT in BVG_MODE_FP32); the reflect
+// padding of the k-tap in_layers is materialised as (k-1)*dil/2 mirrored rows either side of every utterance in the bf16 /
+// fp32 operand copy of x (written by the kernel that updates x), so that the convolution itself needs no edge case.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "conv.cuh"
+
+namespace bvg {
+
+// ------------------------------------------------------------------------------------------------ small kernels ----
+// out[(o / group) * gstride + b * bstride + o % group] = post(bias[o] + bias2[o] + sum_i W[o][i] * pre(x[b][i]));
+// one warp per (b, o).  pre/post: 0 none, 1 SiLU.  Per-utterance vectors only (B rows): timestep MLPs, adaLN, cond_layer.
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+__global__ void rowvec_linear_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ W,
+                                     const float* __restrict__ bias, const float* __restrict__ bias2, int B, int I, int O,
+                                     int pre, int post, int group, int64_t gstride, int64_t bstride) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (wid >= (int64_t)B * O) return;
+  const int b = (int)(wid / O), o = (int)(wid % O);
+  const float* w = W + (int64_t)o * I;
+  const float* xr = x + (int64_t)b * I;
+  float acc = 0.f;
+  for (int i = lane; i < I; i += 32) {
+    float v = xr[i];
+    if (pre == 1) v = silu_f(v);
+    acc = fmaf(w[i], v, acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float y = acc + (bias ? bias[o] : 0.f) + (bias2 ? bias2[o] : 0.f);
+    if (post == 1) y = silu_f(y);
+    out[(int64_t)(o / group) * gstride + (int64_t)b * bstride + (o % group)] = y;
+  }
+}
+
+// TimestepEmbedder.timestep_embedding (diffusion_transformer.py:41-55): args = scale * t[b] * freqs[j]; [cos(args) | sin(args)]
+__global__ void ts_embed_kernel(float* __restrict__ out, const float* __restrict__ t, const float* __restrict__ freqs, int B,
+                                int half, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, j = i % half;
+  const float a = (scale * t[b]) * freqs[j];
+  out[(int64_t)b * 2 * half + j] = cosf(a);
+  out[(int64_t)b * 2 * half + half + j] = sinf(a);
+}
+
+template <typename T>
+__device__ __forceinline__ void st_act(T* p, float v);
+template <>
+__device__ __forceinline__ void st_act<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_act<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// Operand copy of x with mirrored halo rows: xp[b][P + t] = x[b][t] (cast), xp[b][P - q] = x[b][q], xp[b][P + T - 1 + q] =
+// x[b][T - 1 - q] for q = 1..P (F.pad(mode='reflect'), encodec.py:163-176; needs T > P).  Row t of x is written to every
+// padded row that mirrors it by the thread that owns it.
+template <typename T>
+__device__ __forceinline__ void store_reflect(T* xp_b, int64_t Tlen, int P, int H, int64_t t, int c, float v) {
+  st_act(xp_b + (P + t) * H + c, v);
+  if (t >= 1 && t <= P) st_act(xp_b + (P - t) * H + c, v);
+  const int64_t q = Tlen - 1 - t;
+  if (q >= 1 && q <= P) st_act(xp_b + (P + Tlen - 1 + q) * H + c, v);
+}
+
+// after conv1: operand copy of the (unmasked, wavenet.py:141) x and a zeroed skip accumulator
+template <typename T>
+__global__ void wn_prepare_kernel(T* __restrict__ xp, float* __restrict__ skip, const float* __restrict__ x, int B, int64_t Tlen,
+                                  int H, int P) {
+  const int64_t n = (int64_t)B * Tlen * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H);
+    const int64_t r = i / H, t = r % Tlen, b = r / Tlen;
+    store_reflect(xp + b * (Tlen + 2 * P) * H, Tlen, P, H, t, c, BVG_LDG(x + i));
+    skip[i] = 0.f;
+  }
+}
+
+// commons.fused_add_tanh_sigmoid_multiply (commons.py:133-139); the per-utterance cond row g_l and the conv bias are already
+// inside z (bias rows of the in_layer conv).  z: [B][T + 2P][2H] fp32 (rows P .. P+T are the conv outputs), acts: [B][T][H]
+template <typename T>
+__global__ void wn_gate_kernel(T* __restrict__ acts, const float* __restrict__ z, int B, int64_t Tlen, int H, int P) {
+  const int64_t n = (int64_t)B * Tlen * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H);
+    const int64_t r = i / H, t = r % Tlen, b = r / Tlen;
+    const float* zr = z + ((b * (Tlen + 2 * P)) + P + t) * (2 * (int64_t)H);
+    const float ta = tanhf(BVG_LDG(zr + c));
+    const float sg = 1.0f / (1.0f + expf(-BVG_LDG(zr + H + c)));
+    st_act(acts + i, ta * sg);
+  }
+}
+
+// wavenet.py:153-160.  rs: [B][T][2H] (res | skip) or [B][T][H] (last layer: skip only)
+//   not last: x = (x + res) * mask  (+ operand copy with mirrored rows);  skip += rs[H:]
+//   last:     skip = (skip + rs) * mask            (output * x_mask, wavenet.py:161)
+template <typename T>
+__global__ void wn_update_kernel(float* __restrict__ x, T* __restrict__ xp, float* __restrict__ skip, const float* __restrict__ rs,
+                                 const int* __restrict__ lens, int B, int64_t Tlen, int H, int P, int last) {
+  const int64_t n = (int64_t)B * Tlen * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H);
+    const int64_t r = i / H, t = r % Tlen, b = r / Tlen;
+    const float m = (!lens || t < (int64_t)lens[b]) ? 1.f : 0.f;
+    if (last) {
+      skip[i] = (skip[i] + BVG_LDG(rs + r * H + c)) * m;
+    } else {
+      const float* rr = rs + r * (2 * (int64_t)H);
+      const float xv = (x[i] + BVG_LDG(rr + c)) * m;
+      x[i] = xv;
+      store_reflect(xp + b * (Tlen + 2 * P) * H, Tlen, P, H, t, c, xv);
+      skip[i] += BVG_LDG(rr + H + c);
+    }
+  }
+}
+
+// FinalLayer up to its Linear (diffusion_transformer.py:95-97): F.layer_norm over the H channels of a row (biased variance,
+// eps, no affine), then x * (1 + scale[b]) + shift[b].  mod: [B][2H] = (shift | scale).  One warp per row.
+template <typename T>
+__global__ void ln_modulate_kernel(T* __restrict__ out, const float* __restrict__ y, const float* __restrict__ mod, int64_t rows,
+                                   int64_t Tlen, int H, float eps) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float* yr = y + row * H;
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) s += BVG_LDG(yr + c);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  const float mean = s / (float)H;
+  float q = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float d = BVG_LDG(yr + c) - mean;
+    q = fmaf(d, d, q);
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) q += __shfl_xor_sync(0xffffffffu, q, k);
+  const float rstd = rsqrtf(q / (float)H + eps);
+  const float* mb = mod + (row / Tlen) * (2 * (int64_t)H);
+  for (int c = lane; c < H; c += 32) {
+    const float v = (BVG_LDG(yr + c) - mean) * rstd;
+    st_act(out + row * H + c, fmaf(v, mb[H + c], v) + mb[c]);
+  }
+}
+
+// flow_matching.py:103-112, one Euler step in place on x [B][C][T]:
+//   d = c1 * dphi[b] - c2 * dphi[B + b]   (c1 = 1 + cfg_rate, c2 = cfg_rate; the reference's `(1.0 + r) * a - r * b`)
+//   x = x + dt * d;  x[..., :prompt_len] = 0
+// Every product and sum is rounded separately (no FMA contraction): bit-identical to the reference's fp32 tensor ops.
+__global__ void cfm_euler_step_kernel(float* __restrict__ x, const float* __restrict__ dphi, float dt, float c1, float c2, int cfg,
+                                      int64_t n_per_b, int64_t Tlen, int64_t prompt_len, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i % Tlen;
+    float d = BVG_LDG(dphi + i);
+    if (cfg) d = __fsub_rn(__fmul_rn(c1, d), __fmul_rn(c2, BVG_LDG(dphi + n + i)));
+    const float y = __fadd_rn(x[i], __fmul_rn(dt, d));
+    x[i] = t < prompt_len ? 0.f : y;
+  }
+  (void)n_per_b;
+}
+
+static inline unsigned ew_blocks(int64_t n) {
+  const int64_t b = ceil_div(n, 256);
+  return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+struct DenseW {
+  void* w = nullptr;      // packed Wp[k][Cout_r][Cin_p] (conv kernels)
+  float* bias = nullptr;  // [Cout_r]
+  int Cin = 0, Cout = 0, k = 1, dil = 1, Cin_p = 0, Cout_n = 0, Cout_r = 0;
+  bool has_w = false, has_b = false;
+};
+struct VecW {             // fp32 [O][I] row-vector layers
+  float* w = nullptr;
+  float* b = nullptr;
+  int I = 0, O = 0;
+  bool has_w = false, has_b = false;
+};
+
+}  // namespace bvg
+
+using namespace bvg;
+
+struct bvg_s2mel_tail {
+  bvg_s2mel_config cfg;
+  int act_dt = BVG_BF16;
+  int P = 0;                       // mirrored rows either side: (k - 1) / 2 (dilation_rate 1 -> every layer the same)
+  DenseW conv1, res_proj, fin_linear, conv2;
+  std::vector<DenseW> in_layers, res_skip;
+  VecW te_l0, te_l2, cond, adaln;
+  float* freqs = nullptr;          // [freq_dim / 2]
+  float* in_bias_cat = nullptr;    // [n_layers][2H]: the in_layer biases, added to the cond rows
+  bool has_freqs = false;
+  bool finalized = false;
+  // workspace
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  int own_sm = 1;
+};
+
+namespace bvg {
+
+static void init_dense(DenseW& d, int Cin, int Cout, int k, int dil) {
+  d.Cin = Cin; d.Cout = Cout; d.k = k; d.dil = dil;
+  d.Cin_p = pad_channels(Cin);
+  d.Cout_n = pad_channels(Cout);
+  d.Cout_r = round_up(d.Cout_n, 128);
+}
+static int alloc_dense(DenseW& d, int dt) {
+  BVG_CUDA(cudaMalloc(&d.w, (size_t)d.k * d.Cout_r * d.Cin_p * dtype_size(dt)));
+  BVG_CUDA(cudaMalloc((void**)&d.bias, (size_t)d.Cout_r * 4));
+  BVG_CUDA(cudaMemset(d.bias, 0, (size_t)d.Cout_r * 4));
+  return BVG_OK;
+}
+static int alloc_vec(VecW& v, int I, int O) {
+  v.I = I; v.O = O;
+  BVG_CUDA(cudaMalloc((void**)&v.w, (size_t)I * O * 4));
+  BVG_CUDA(cudaMalloc((void**)&v.b, (size_t)O * 4));
+  BVG_CUDA(cudaMemset(v.b, 0, (size_t)O * 4));
+  return BVG_OK;
+}
+static void free_dense(DenseW& d) { cudaFree(d.w); cudaFree(d.bias); }
+static void free_vec(VecW& v) { cudaFree(v.w); cudaFree(v.b); }
+
+static int set_dense(bvg_s2mel_tail* h, DenseW& d, bool is_w, const float* dev, int64_t numel, const char* name) {
+  if (is_w) {
+    const int64_t want = (int64_t)d.Cin * d.Cout * d.k;
+    if (numel != want) BVG_FAIL(BVG_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)want, (long long)numel);
+    const int rc = pack_conv_weight(d.w, h->act_dt, dev, d.Cout, d.Cin, d.k, d.Cout_r, d.Cin_p, 0);
+    if (rc) return rc;
+    d.has_w = true;
+  } else {
+    if (numel != d.Cout) BVG_FAIL(BVG_EINVAL, "%s: expected %d elements, got %lld", name, d.Cout, (long long)numel);
+    BVG_CUDA(cudaMemcpy(d.bias, dev, (size_t)d.Cout * 4, cudaMemcpyDeviceToDevice));
+    d.has_b = true;
+  }
+  return BVG_OK;
+}
+static int set_vec(VecW& v, bool is_w, const float* dev, int64_t numel, const char* name) {
+  const int64_t want = is_w ? (int64_t)v.I * v.O : v.O;
+  if (numel != want) BVG_FAIL(BVG_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)want, (long long)numel);
+  BVG_CUDA(cudaMemcpy(is_w ? v.w : v.b, dev, (size_t)numel * 4, cudaMemcpyDeviceToDevice));
+  (is_w ? v.has_w : v.has_b) = true;
+  return BVG_OK;
+}
+
+static bool eat_s(const char*& s, const char* prefix) {
+  const size_t n = strlen(prefix);
+  if (strncmp(s, prefix, n)) return false;
+  s += n;
+  return true;
+}
+static bool parse_idx(const char*& s, int* out) {
+  int v = 0, nd = 0;
+  while (*s >= '0' && *s <= '9' && nd < 4) { v = v * 10 + (*s - '0'); ++s; ++nd; }
+  if (!nd || (*s >= '0' && *s <= '9')) return false;
+  *out = v;
+  return true;
+}
+
+static int run_dense(bvg_s2mel_tail* h, const DenseW& d, const void* in, void* out, int out_dt, const float* res, const float* bias_rows,
+                     int B, int64_t T, cudaStream_t st) {
+  ConvArgs a;
+  a.in = in; a.w = d.w; a.bias = d.bias; a.out = out; a.res = res; a.accum = nullptr; a.scale = 1.f;
+  if (bias_rows) { a.bias = bias_rows; a.bias_bs = d.Cout_r; }
+  a.in_dtype = h->act_dt; a.w_dtype = h->act_dt; a.out_dtype = out_dt;
+  a.B = B; a.T = T; a.Cin_p = d.Cin_p; a.Cout_n = d.Cout_n; a.Cout_r = d.Cout_r; a.out_ld = d.Cout_n;
+  a.k = d.k; a.dil = d.dil; a.own_sm = h->own_sm;
+  if (h->cfg.mode == BVG_MODE_BF16 && conv_umma_supported(a)) return conv_umma_launch(a, 0, st);
+  return conv_simt_launch(a, st);
+}
+
+static int run_vec(const VecW& v, float* out, const float* x, const float* bias2, int B, int pre, int post, int group, int64_t gstride,
+                   int64_t bstride, cudaStream_t st) {
+  const int64_t warps = (int64_t)B * v.O;
+  rowvec_linear_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, st>>>(out, x, v.w, v.b, bias2, B, v.I, v.O, pre, post, group,
+                                                                            gstride, bstride);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+struct TailBufs {
+  float *temb, *t2a, *t2, *mod, *brows, *x, *skip, *z, *rs, *y, *o;
+  void *xr, *xp, *acts, *yb, *hb;
+  size_t total;
+};
+static TailBufs plan_tail(const bvg_s2mel_tail* h, unsigned char* base, int B, int64_t T) {
+  const int H = h->cfg.hidden, L = h->cfg.n_layers, P = h->P;
+  const size_t es = dtype_size(h->act_dt);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  TailBufs b;
+  const size_t rows = (size_t)B * T, prow = (size_t)B * (T + 2 * P);
+  const int Co = pad_channels(h->cfg.out_channels);
+#define BVG_TAKE(field, type, bytes) { const size_t o_ = take(bytes); b.field = base ? (type)(base + o_) : nullptr; }
+  BVG_TAKE(temb, float*, (size_t)B * h->cfg.freq_dim * 4);
+  BVG_TAKE(t2a, float*, (size_t)B * H * 4);
+  BVG_TAKE(t2, float*, (size_t)B * H * 4);
+  BVG_TAKE(mod, float*, (size_t)B * 2 * H * 4);
+  BVG_TAKE(brows, float*, (size_t)L * B * h->in_layers[0].Cout_r * 4);
+  BVG_TAKE(xr, void*, rows * h->conv1.Cin_p * es);
+  BVG_TAKE(x, float*, rows * H * 4);
+  BVG_TAKE(skip, float*, rows * H * 4);
+  BVG_TAKE(xp, void*, prow * H * es);
+  BVG_TAKE(z, float*, prow * 2 * H * 4);
+  BVG_TAKE(acts, void*, rows * H * es);
+  BVG_TAKE(rs, float*, rows * 2 * H * 4);
+  BVG_TAKE(y, float*, rows * H * 4);
+  BVG_TAKE(yb, void*, rows * H * es);
+  BVG_TAKE(hb, void*, rows * H * es);
+  BVG_TAKE(o, float*, rows * Co * 4);
+#undef BVG_TAKE
+  b.total = off;
+  return b;
+}
+
+}  // namespace bvg
+
+// ------------------------------------------------------------------------------------------------------- C ABI ----
+extern "C" int bvg_s2mel_tail_create(const bvg_s2mel_config* cfg, bvg_s2mel_tail** out) {
+  if (!cfg || !out) BVG_FAIL(BVG_EINVAL, "bvg_s2mel_tail_create: null argument");
+  if (cfg->hidden <= 0 || cfg->hidden % 16 || cfg->dit_hidden <= 0 || cfg->dit_hidden % 16)
+    BVG_FAIL(BVG_EINVAL, "hidden sizes must be positive multiples of 16");
+  if (cfg->n_layers < 1 || cfg->n_layers > 64) BVG_FAIL(BVG_EINVAL, "n_layers out of range");
+  if (cfg->kernel_size < 1 || cfg->kernel_size % 2 == 0) BVG_FAIL(BVG_EINVAL, "kernel_size must be odd (wavenet.py:106)");
+  if (cfg->dilation_rate != 1)
+    BVG_FAIL(BVG_EINVAL, "dilation_rate %d: only 1 (the IndexTTS2 s2mel configuration) is built", cfg->dilation_rate);
+  if (cfg->out_channels <= 0 || cfg->freq_dim <= 0 || cfg->freq_dim % 2) BVG_FAIL(BVG_EINVAL, "bad out_channels / freq_dim");
+  if (cfg->mode != BVG_MODE_FP32 && cfg->mode != BVG_MODE_BF16) BVG_FAIL(BVG_EINVAL, "unknown precision mode");
+  BVG_DEVICE(cfg->device);
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  bvg_s2mel_tail* h = new (std::nothrow) bvg_s2mel_tail();
+  if (!h) BVG_FAIL(BVG_ENOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->act_dt = cfg->mode == BVG_MODE_BF16 ? BVG_BF16 : BVG_F32;
+  h->P = (cfg->kernel_size - 1) / 2;
+  const int H = cfg->hidden, D = cfg->dit_hidden, L = cfg->n_layers;
+  init_dense(h->conv1, D, H, 1, 1);
+  init_dense(h->res_proj, D, H, 1, 1);
+  init_dense(h->fin_linear, H, H, 1, 1);
+  init_dense(h->conv2, H, cfg->out_channels, 1, 1);
+  h->in_layers.resize(L);
+  h->res_skip.resize(L);
+  rc = alloc_dense(h->conv1, h->act_dt);
+  if (!rc) rc = alloc_dense(h->res_proj, h->act_dt);
+  if (!rc) rc = alloc_dense(h->fin_linear, h->act_dt);
+  if (!rc) rc = alloc_dense(h->conv2, h->act_dt);
+  for (int i = 0; i < L && !rc; ++i) {
+    init_dense(h->in_layers[i], H, 2 * H, cfg->kernel_size, 1);
+    init_dense(h->res_skip[i], H, i < L - 1 ? 2 * H : H, 1, 1);
+    rc = alloc_dense(h->in_layers[i], h->act_dt);
+    if (!rc) rc = alloc_dense(h->res_skip[i], h->act_dt);
+  }
+  if (!rc) rc = alloc_vec(h->te_l0, cfg->freq_dim, H);
+  if (!rc) rc = alloc_vec(h->te_l2, H, H);
+  if (!rc) rc = alloc_vec(h->cond, H, 2 * H * L);
+  if (!rc) rc = alloc_vec(h->adaln, H, 2 * H);
+  if (!rc && cudaMalloc((void**)&h->freqs, (size_t)cfg->freq_dim / 2 * 4) != cudaSuccess) rc = BVG_ENOMEM;
+  if (!rc && cudaMalloc((void**)&h->in_bias_cat, (size_t)L * 2 * H * 4) != cudaSuccess) rc = BVG_ENOMEM;
+  if (rc) { bvg_s2mel_tail_destroy(h); return rc; }
+  *out = h;
+  return BVG_OK;
+}
+
+extern "C" void bvg_s2mel_tail_destroy(bvg_s2mel_tail* h) {
+  if (!h) return;
+  DeviceGuard g(h->cfg.device);
+  cudaDeviceSynchronize();
+  free_dense(h->conv1); free_dense(h->res_proj); free_dense(h->fin_linear); free_dense(h->conv2);
+  for (auto& d : h->in_layers) free_dense(d);
+  for (auto& d : h->res_skip) free_dense(d);
+  free_vec(h->te_l0); free_vec(h->te_l2); free_vec(h->cond); free_vec(h->adaln);
+  cudaFree(h->freqs);
+  cudaFree(h->in_bias_cat);
+  cudaFree(h->arena);
+  delete h;
+}
+
+extern "C" int bvg_s2mel_tail_set_tensor(bvg_s2mel_tail* h, const char* name, const float* data, int64_t numel, int is_device) {
+  if (!h || !name || !data || numel <= 0) BVG_FAIL(BVG_EINVAL, "bvg_s2mel_tail_set_tensor: bad argument");
+  BVG_DEVICE(h->cfg.device);
+  float* tmp = nullptr;
+  const float* d = data;
+  if (!is_device) {
+    BVG_CUDA(cudaMalloc((void**)&tmp, numel * sizeof(float)));
+    cudaError_t e = cudaMemcpy(tmp, data, numel * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(tmp); BVG_CUDA(e); }
+    d = tmp;
+  }
+  int rc = BVG_EINVAL;
+  const char* s = name;
+  int i = 0;
+  auto wb = [&](const char* rest, bool* is_w) {
+    if (!strcmp(rest, "weight")) { *is_w = true; return true; }
+    if (!strcmp(rest, "bias")) { *is_w = false; return true; }
+    return false;
+  };
+  bool is_w = false, known = true;
+  if (eat_s(s, "conv1.") && wb(s, &is_w)) rc = set_dense(h, h->conv1, is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "res_projection.")) && wb(s, &is_w)) rc = set_dense(h, h->res_proj, is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "final_layer.linear.")) && wb(s, &is_w)) rc = set_dense(h, h->fin_linear, is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "conv2.")) && wb(s, &is_w)) rc = set_dense(h, h->conv2, is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "final_layer.adaLN_modulation.1.")) && wb(s, &is_w)) rc = set_vec(h->adaln, is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "t_embedder2.mlp.0.")) && wb(s, &is_w)) rc = set_vec(h->te_l0, is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "t_embedder2.mlp.2.")) && wb(s, &is_w)) rc = set_vec(h->te_l2, is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "wavenet.cond_layer.")) && wb(s, &is_w)) rc = set_vec(h->cond, is_w, d, numel, name);
+  else if (!strcmp(name, "t_embedder2.freqs")) {
+    if (numel != h->cfg.freq_dim / 2) { set_error("%s: expected %d elements", name, h->cfg.freq_dim / 2); rc = BVG_EINVAL; }
+    else {
+      cudaError_t e = cudaMemcpy(h->freqs, d, (size_t)numel * 4, cudaMemcpyDeviceToDevice);
+      if (e != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(e)); rc = BVG_ECUDA; }
+      else { h->has_freqs = true; rc = BVG_OK; }
+    }
+  } else if ((s = name, eat_s(s, "wavenet.in_layers.")) && parse_idx(s, &i) && i < h->cfg.n_layers && eat_s(s, ".") && wb(s, &is_w))
+    rc = set_dense(h, h->in_layers[i], is_w, d, numel, name);
+  else if ((s = name, eat_s(s, "wavenet.res_skip_layers.")) && parse_idx(s, &i) && i < h->cfg.n_layers && eat_s(s, ".") && wb(s, &is_w))
+    rc = set_dense(h, h->res_skip[i], is_w, d, numel, name);
+  else known = false;
+  if (!known) { set_error("unknown tensor name '%s'", name); rc = BVG_EINVAL; }
+  cudaError_t e = cudaDeviceSynchronize();   // pack kernels read `d`
+  if (tmp) cudaFree(tmp);
+  if (rc) return rc;
+  BVG_CUDA(e);
+  h->finalized = false;
+  return BVG_OK;
+}
+
+extern "C" int bvg_s2mel_tail_finalize(bvg_s2mel_tail* h) {
+  if (!h) BVG_FAIL(BVG_EINVAL, "null handle");
+  std::string missing;
+  auto need = [&](bool ok, const std::string& n) { if (!ok) missing += (missing.empty() ? "" : ", ") + n; };
+  need(h->conv1.has_w && h->conv1.has_b, "conv1");
+  need(h->res_proj.has_w && h->res_proj.has_b, "res_projection");
+  need(h->fin_linear.has_w && h->fin_linear.has_b, "final_layer.linear");
+  need(h->conv2.has_w && h->conv2.has_b, "conv2");
+  need(h->adaln.has_w && h->adaln.has_b, "final_layer.adaLN_modulation.1");
+  need(h->te_l0.has_w && h->te_l0.has_b, "t_embedder2.mlp.0");
+  need(h->te_l2.has_w && h->te_l2.has_b, "t_embedder2.mlp.2");
+  need(h->cond.has_w && h->cond.has_b, "wavenet.cond_layer");
+  need(h->has_freqs, "t_embedder2.freqs");
+  for (int i = 0; i < h->cfg.n_layers; ++i) {
+    need(h->in_layers[i].has_w && h->in_layers[i].has_b, "wavenet.in_layers." + std::to_string(i));
+    need(h->res_skip[i].has_w && h->res_skip[i].has_b, "wavenet.res_skip_layers." + std::to_string(i));
+  }
+  if (!missing.empty()) BVG_FAIL(BVG_ESTATE, "missing tensors: %s", missing.c_str());
+  BVG_DEVICE(h->cfg.device);
+  for (int i = 0; i < h->cfg.n_layers; ++i)
+    BVG_CUDA(cudaMemcpy(h->in_bias_cat + (size_t)i * 2 * h->cfg.hidden, h->in_layers[i].bias, (size_t)2 * h->cfg.hidden * 4,
+                        cudaMemcpyDeviceToDevice));
+  h->finalized = true;
+  return BVG_OK;
+}
+
+extern "C" int64_t bvg_s2mel_tail_workspace_bytes(const bvg_s2mel_tail* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return (int64_t)plan_tail(h, nullptr, B, T).total;
+}
+
+extern "C" int bvg_s2mel_tail_fwd(bvg_s2mel_tail* h, const float* x_res, const int* x_lens, const float* t, const float* t1,
+                                  float* out, int B, int T, bvg_stream_t stream) {
+  if (!h || !h->finalized) BVG_FAIL(BVG_ESTATE, "s2mel tail handle is not finalized");
+  if (B < 0 || T < 0) BVG_FAIL(BVG_EINVAL, "negative batch or length");
+  if (B == 0 || T == 0) return BVG_OK;
+  if (!x_res || !t || !t1 || !out) BVG_FAIL(BVG_EINVAL, "null pointer");
+  if (T <= h->P) BVG_FAIL(BVG_EINVAL, "T = %d: reflect padding of the k = %d in_layers needs T > %d", T, h->cfg.kernel_size, h->P);
+  BVG_DEVICE(h->cfg.device);
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->cfg.hidden, L = h->cfg.n_layers, P = h->P, D = h->cfg.dit_hidden;
+  {
+    const size_t need = plan_tail(h, nullptr, B, T).total;
+    if (need > h->arena_bytes) {
+      if (h->arena) { BVG_CUDA(cudaDeviceSynchronize()); cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; }
+      BVG_CUDA(cudaMalloc((void**)&h->arena, need));
+      h->arena_bytes = need;
+    }
+  }
+  const TailBufs bf = plan_tail(h, h->arena, B, T);
+  const int64_t rows = (int64_t)B * T;
+  const bool bf16 = h->act_dt == BVG_BF16;
+  const int Cr = h->in_layers[0].Cout_r;
+
+  // per-utterance vectors: t2 = t_embedder2(t); cond rows g_l + in_layer bias; (shift | scale) = adaLN(SiLU(t1))
+  const int half = h->cfg.freq_dim / 2;
+  ts_embed_kernel<<<(unsigned)ceil_div((int64_t)B * half, 128), 128, 0, st>>>(bf.temb, t, h->freqs, B, half, 1000.0f);
+  BVG_LAUNCHED();
+  if ((rc = run_vec(h->te_l0, bf.t2a, bf.temb, nullptr, B, 0, 1, H, 0, H, st))) return rc;
+  if ((rc = run_vec(h->te_l2, bf.t2, bf.t2a, nullptr, B, 0, 0, H, 0, H, st))) return rc;
+  // cond_layer output channel o = layer * 2H + c  ->  brows[layer][b][c] = cond(t2)[o] + in_layers[layer].bias[c]
+  BVG_CUDA(cudaMemsetAsync(bf.brows, 0, (size_t)L * B * Cr * 4, st));
+  if ((rc = run_vec(h->cond, bf.brows, bf.t2, h->in_bias_cat, B, 0, 0, 2 * H, (int64_t)B * Cr, Cr, st))) return rc;
+  if ((rc = run_vec(h->adaln, bf.mod, t1, nullptr, B, 1, 0, 2 * H, 0, 2 * H, st))) return rc;
+
+  // x = conv1(x_res)
+  const void* xr = x_res;
+  if (bf16 || h->conv1.Cin_p != D) {
+    if ((rc = btc_pad_cast(bf.xr, h->act_dt, x_res, rows, D, h->conv1.Cin_p, st))) return rc;
+    xr = bf.xr;
+  }
+  if ((rc = run_dense(h, h->conv1, xr, bf.x, BVG_F32, nullptr, nullptr, B, T, st))) return rc;
+  if (bf16) wn_prepare_kernel<__nv_bfloat16><<<ew_blocks(rows * H), 256, 0, st>>>((__nv_bfloat16*)bf.xp, bf.skip, bf.x, B, T, H, P);
+  else wn_prepare_kernel<float><<<ew_blocks(rows * H), 256, 0, st>>>((float*)bf.xp, bf.skip, bf.x, B, T, H, P);
+  BVG_LAUNCHED();
+
+  for (int i = 0; i < L; ++i) {
+    // bias rows of this layer: in_layer bias + cond row g_l of every utterance (written above)
+    float* br = bf.brows + (size_t)i * B * Cr;
+    if ((rc = run_dense(h, h->in_layers[i], bf.xp, bf.z, BVG_F32, nullptr, br, B, (int64_t)T + 2 * P, st))) return rc;
+    if (bf16) wn_gate_kernel<__nv_bfloat16><<<ew_blocks(rows * H), 256, 0, st>>>((__nv_bfloat16*)bf.acts, bf.z, B, T, H, P);
+    else wn_gate_kernel<float><<<ew_blocks(rows * H), 256, 0, st>>>((float*)bf.acts, bf.z, B, T, H, P);
+    BVG_LAUNCHED();
+    if ((rc = run_dense(h, h->res_skip[i], bf.acts, bf.rs, BVG_F32, nullptr, nullptr, B, T, st))) return rc;
+    const int last = i == L - 1;
+    if (bf16) wn_update_kernel<__nv_bfloat16><<<ew_blocks(rows * H), 256, 0, st>>>(bf.x, (__nv_bfloat16*)bf.xp, bf.skip, bf.rs, x_lens, B, T, H, P, last);
+    else wn_update_kernel<float><<<ew_blocks(rows * H), 256, 0, st>>>(bf.x, (float*)bf.xp, bf.skip, bf.rs, x_lens, B, T, H, P, last);
+    BVG_LAUNCHED();
+  }
+  // y = wavenet(...)^T + res_projection(x_res)   (the skip sum rides in as the conv's residual operand)
+  if ((rc = run_dense(h, h->res_proj, xr, bf.y, BVG_F32, bf.skip, nullptr, B, T, st))) return rc;
+  // final_layer: LayerNorm -> modulate -> Linear;  conv2;  [B, T, C] -> [B, C, T]
+  {
+    const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+    if (bf16) ln_modulate_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)bf.yb, bf.y, bf.mod, rows, T, H, 1e-6f);
+    else ln_modulate_kernel<float><<<blocks, 256, 0, st>>>((float*)bf.yb, bf.y, bf.mod, rows, T, H, 1e-6f);
+    BVG_LAUNCHED();
+  }
+  if ((rc = run_dense(h, h->fin_linear, bf.yb, bf.hb, h->act_dt, nullptr, nullptr, B, T, st))) return rc;
+  if ((rc = run_dense(h, h->conv2, bf.hb, bf.o, BVG_F32, nullptr, nullptr, B, T, st))) return rc;
+  return btc_to_bct(out, bf.o, BVG_F32, B, h->cfg.out_channels, h->conv2.Cout_n, T, st);
+}
+
+extern "C" int bvg_cfm_euler_step(float* x, const float* dphi, float dt, double cfg_rate, int B, int C, int64_t T, int64_t prompt_len,
+                                  bvg_stream_t stream) {
+  if (B < 0 || C < 0 || T < 0 || prompt_len < 0) BVG_FAIL(BVG_EINVAL, "negative size");
+  if (B == 0 || C == 0 || T == 0) return BVG_OK;
+  if (!x || !dphi) BVG_FAIL(BVG_EINVAL, "null pointer");
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  const int64_t n = (int64_t)B * C * T;
+  // the reference multiplies fp32 tensors by the Python floats (1.0 + r) and r: both are rounded to fp32 first
+  const float c1 = (float)(1.0 + cfg_rate), c2 = (float)cfg_rate;
+  cfm_euler_step_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, dphi, dt, c1, c2, cfg_rate > 0.0 ? 1 : 0, (int64_t)C * T, T,
+                                                                        prompt_len, n);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}

@@ -163,3 +163,46 @@ def make_speaker_embedding(batch, dim, first_utterance=0):
         g.manual_seed(3000 + first_utterance + b)
         out[b] = torch.randn(dim, generator=g)
     return out
+
+
+# ---- s2mel tail (SURVEY.md section 8(f) rank 3) -------------------------------------------------------------------
+def s2mel_tail_spec(cfg):
+    """[(key, shape, fan_in)] of the FOLDED tail weights, keys relative to the reference's DiT module with the
+    `.conv.conv` nesting of encodec.SConv1d dropped (diffusion_transformer.py:139-157, wavenet.py:119-138)."""
+    H, D, L, k = cfg["hidden"], cfg["dit_hidden"], cfg["n_layers"], cfg["kernel_size"]
+    F, C = cfg["freq_dim"], cfg["out_channels"]
+    spec = [("conv1.weight", (H, D), D), ("conv1.bias", (H,), D),
+            ("t_embedder2.mlp.0.weight", (H, F), F), ("t_embedder2.mlp.0.bias", (H,), F),
+            ("t_embedder2.mlp.2.weight", (H, H), H), ("t_embedder2.mlp.2.bias", (H,), H),
+            ("wavenet.cond_layer.weight", (2 * H * L, H, 1), H), ("wavenet.cond_layer.bias", (2 * H * L,), H)]
+    for i in range(L):
+        spec.append(("wavenet.in_layers.%d.weight" % i, (2 * H, H, k), H * k))
+        spec.append(("wavenet.in_layers.%d.bias" % i, (2 * H,), H * k))
+        co = 2 * H if i < L - 1 else H
+        spec.append(("wavenet.res_skip_layers.%d.weight" % i, (co, H, 1), H))
+        spec.append(("wavenet.res_skip_layers.%d.bias" % i, (co,), H))
+    spec += [("res_projection.weight", (H, D), D), ("res_projection.bias", (H,), D),
+             ("final_layer.adaLN_modulation.1.weight", (2 * H, H), H), ("final_layer.adaLN_modulation.1.bias", (2 * H,), H),
+             ("final_layer.linear.weight", (H, H), H), ("final_layer.linear.bias", (H,), H),
+             ("conv2.weight", (C, H, 1), H), ("conv2.bias", (C,), H)]
+    return spec
+
+
+def make_s2mel_tail_state_dict(cfg, seed=4321):
+    """Random-init folded weights, U(-1/sqrt(fan_in), 1/sqrt(fan_in)) like torch's defaults, plus the `freqs` buffer of
+    TimestepEmbedder (diffusion_transformer.py:33-37)."""
+    sd = {key: _uniform(shape, 1.0 / math.sqrt(fan_in), seed, key) for key, shape, fan_in in s2mel_tail_spec(cfg)}
+    half = cfg["freq_dim"] // 2
+    sd["t_embedder2.freqs"] = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+    return sd
+
+
+def make_s2mel_tail_inputs(cfg, B, T, seed=77, lens=None):
+    """x_res ~ N(0, 1) [B, T, dit_hidden], t in (0, 1) [B], t1 ~ N(0, 1) [B, hidden], x_lens [B] int32."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    x_res = torch.randn(B, T, cfg["dit_hidden"], generator=g)
+    t = torch.rand(B, generator=g)
+    t1 = torch.randn(B, cfg["hidden"], generator=g)
+    x_lens = torch.tensor(lens if lens is not None else [T] * B, dtype=torch.int32)
+    return x_res, t, t1, x_lens
