@@ -257,6 +257,10 @@ int64_t bvg_s2mel_tail_workspace_bytes(const bvg_s2mel_tail* h, int B, int T);
  * All device pointers; T > (kernel_size - 1) / 2. */
 int bvg_s2mel_tail_fwd(bvg_s2mel_tail* h, const float* x_res, const int* x_lens, const float* t, const float* t1, float* out,
                        int B, int T, bvg_stream_t stream);
+/* options: "graph" (0 never, 1 always, 2 [default] from the second forward of a (B, T) shape on: the launch sequence replays
+ * as one CUDA graph - the solver calls the estimator 25 times per utterance with one shape), "conv_own_sm" (as bvg_set_option) */
+int bvg_s2mel_tail_set_option(bvg_s2mel_tail* h, const char* key, int value);
+int bvg_s2mel_tail_last_forward_launches(const bvg_s2mel_tail* h);
 /* One Euler step of BASECFM.solve_euler in place on x [B, C, T] fp32 (device):
  *   cfg_rate > 0: dphi is the stacked estimator output [2B, C, T]; d = (1 + cfg_rate) * dphi[:B] - cfg_rate * dphi[B:]
  *   else        : dphi is [B, C, T]; d = dphi

@@ -35,7 +35,16 @@ for prec in ("bf16", "fp32"):
             e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) / 20)
     ms = statistics.median(ts)
-    out[prec] = {"ms_per_call": ms, "tflops": flops / (ms * 1e-3) / 1e12, "launches": int(launches), "frames_per_s": B * T / (ms * 1e-3)}
+    m.set_option("graph", 0)
+    with torch.no_grad():
+        for _ in range(3): y2 = m(xr, ld, td, t1d)
+        torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20): y2 = m(xr, ld, td, t1d)
+        e1.record(); torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1) / 20
+    assert torch.equal(y, y2)
+    out[prec] = {"ms_per_call": ms, "ms_per_call_without_graph_replay": eager_ms, "tflops": flops / (ms * 1e-3) / 1e12, "launches": int(launches), "frames_per_s": B * T / (ms * 1e-3)}
     if prec == "fp32": ref = y.cpu()
     else: yb = y.cpu()
 from oracle import bigvgan_oracle as O

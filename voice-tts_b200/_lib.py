@@ -71,6 +71,8 @@ SYMBOLS = {
     "bvg_s2mel_tail_finalize": (_i, [_vp]),
     "bvg_s2mel_tail_workspace_bytes": (_i64, [_vp, _i, _i]),
     "bvg_s2mel_tail_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "bvg_s2mel_tail_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
+    "bvg_s2mel_tail_last_forward_launches": (_i, [_vp]),
     "bvg_cfm_euler_step": (_i, [_vp, _vp, _f, ctypes.c_double, _i, _i, _i64, _i64, _vp]),
 }
 

@@ -16,7 +16,9 @@
 // padding of the k-tap in_layers is materialised as (k-1)*dil/2 mirrored rows either side of every utterance in the bf16 /
 // fp32 operand copy of x (written by the kernel that updates x), so that the convolution itself needs no edge case.
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "conv.cuh"
@@ -214,6 +216,10 @@ struct bvg_s2mel_tail {
   unsigned char* arena = nullptr;
   size_t arena_bytes = 0;
   int own_sm = 1;
+  int opt_graph = 2;               // CUDA-graph replay: 0 never, 1 from the first forward of a shape, 2 from the second
+  int last_launches = 0;
+  std::map<std::tuple<int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;   // (B, T, has_lens) -> exec + kernels inside
+  std::map<std::tuple<int, int, int>, int> seen;
 };
 
 namespace bvg {
@@ -298,7 +304,8 @@ static int run_vec(const VecW& v, float* out, const float* x, const float* bias2
 }
 
 struct TailBufs {
-  float *temb, *t2a, *t2, *mod, *brows, *x, *skip, *z, *rs, *y, *o;
+  float *t_in, *t1_in, *temb, *t2a, *t2, *mod, *brows, *x, *skip, *z, *rs, *y, *o;
+  int* lens_in;
   void *xr, *xp, *acts, *yb, *hb;
   size_t total;
 };
@@ -311,6 +318,9 @@ static TailBufs plan_tail(const bvg_s2mel_tail* h, unsigned char* base, int B, i
   const size_t rows = (size_t)B * T, prow = (size_t)B * (T + 2 * P);
   const int Co = pad_channels(h->cfg.out_channels);
 #define BVG_TAKE(field, type, bytes) { const size_t o_ = take(bytes); b.field = base ? (type)(base + o_) : nullptr; }
+  BVG_TAKE(t_in, float*, (size_t)B * 4);
+  BVG_TAKE(t1_in, float*, (size_t)B * H * 4);
+  BVG_TAKE(lens_in, int*, (size_t)B * 4);
   BVG_TAKE(temb, float*, (size_t)B * h->cfg.freq_dim * 4);
   BVG_TAKE(t2a, float*, (size_t)B * H * 4);
   BVG_TAKE(t2, float*, (size_t)B * H * 4);
@@ -389,6 +399,7 @@ extern "C" void bvg_s2mel_tail_destroy(bvg_s2mel_tail* h) {
   for (auto& d : h->in_layers) free_dense(d);
   for (auto& d : h->res_skip) free_dense(d);
   free_vec(h->te_l0); free_vec(h->te_l2); free_vec(h->cond); free_vec(h->adaln);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
   cudaFree(h->freqs);
   cudaFree(h->in_bias_cat);
   cudaFree(h->arena);
@@ -475,49 +486,29 @@ extern "C" int64_t bvg_s2mel_tail_workspace_bytes(const bvg_s2mel_tail* h, int B
   return (int64_t)plan_tail(h, nullptr, B, T).total;
 }
 
-extern "C" int bvg_s2mel_tail_fwd(bvg_s2mel_tail* h, const float* x_res, const int* x_lens, const float* t, const float* t1,
-                                  float* out, int B, int T, bvg_stream_t stream) {
-  if (!h || !h->finalized) BVG_FAIL(BVG_ESTATE, "s2mel tail handle is not finalized");
-  if (B < 0 || T < 0) BVG_FAIL(BVG_EINVAL, "negative batch or length");
-  if (B == 0 || T == 0) return BVG_OK;
-  if (!x_res || !t || !t1 || !out) BVG_FAIL(BVG_EINVAL, "null pointer");
-  if (T <= h->P) BVG_FAIL(BVG_EINVAL, "T = %d: reflect padding of the k = %d in_layers needs T > %d", T, h->cfg.kernel_size, h->P);
-  BVG_DEVICE(h->cfg.device);
-  int rc = ensure_device_ok();
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int H = h->cfg.hidden, L = h->cfg.n_layers, P = h->P, D = h->cfg.dit_hidden;
-  {
-    const size_t need = plan_tail(h, nullptr, B, T).total;
-    if (need > h->arena_bytes) {
-      if (h->arena) { BVG_CUDA(cudaDeviceSynchronize()); cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; }
-      BVG_CUDA(cudaMalloc((void**)&h->arena, need));
-      h->arena_bytes = need;
-    }
-  }
-  const TailBufs bf = plan_tail(h, h->arena, B, T);
+namespace bvg {
+// Everything between the staged inputs (bf.t_in, bf.t1_in, bf.lens_in, bf.xr) and the channels-last result bf.o: touches arena
+// memory only, so the launch sequence of a (B, T) shape can be captured once and replayed as a CUDA graph.
+static int tail_body(bvg_s2mel_tail* h, const TailBufs& bf, int B, int T, bool has_lens, cudaStream_t st) {
+  const int H = h->cfg.hidden, L = h->cfg.n_layers, P = h->P;
   const int64_t rows = (int64_t)B * T;
   const bool bf16 = h->act_dt == BVG_BF16;
   const int Cr = h->in_layers[0].Cout_r;
-
+  const int* lens = has_lens ? bf.lens_in : nullptr;
+  int rc;
   // per-utterance vectors: t2 = t_embedder2(t); cond rows g_l + in_layer bias; (shift | scale) = adaLN(SiLU(t1))
   const int half = h->cfg.freq_dim / 2;
-  ts_embed_kernel<<<(unsigned)ceil_div((int64_t)B * half, 128), 128, 0, st>>>(bf.temb, t, h->freqs, B, half, 1000.0f);
+  ts_embed_kernel<<<(unsigned)ceil_div((int64_t)B * half, 128), 128, 0, st>>>(bf.temb, bf.t_in, h->freqs, B, half, 1000.0f);
   BVG_LAUNCHED();
   if ((rc = run_vec(h->te_l0, bf.t2a, bf.temb, nullptr, B, 0, 1, H, 0, H, st))) return rc;
   if ((rc = run_vec(h->te_l2, bf.t2, bf.t2a, nullptr, B, 0, 0, H, 0, H, st))) return rc;
   // cond_layer output channel o = layer * 2H + c  ->  brows[layer][b][c] = cond(t2)[o] + in_layers[layer].bias[c]
-  BVG_CUDA(cudaMemsetAsync(bf.brows, 0, (size_t)L * B * Cr * 4, st));
+  if (Cr != 2 * H) BVG_CUDA(cudaMemsetAsync(bf.brows, 0, (size_t)L * B * Cr * 4, st));
   if ((rc = run_vec(h->cond, bf.brows, bf.t2, h->in_bias_cat, B, 0, 0, 2 * H, (int64_t)B * Cr, Cr, st))) return rc;
-  if ((rc = run_vec(h->adaln, bf.mod, t1, nullptr, B, 1, 0, 2 * H, 0, 2 * H, st))) return rc;
+  if ((rc = run_vec(h->adaln, bf.mod, bf.t1_in, nullptr, B, 1, 0, 2 * H, 0, 2 * H, st))) return rc;
 
   // x = conv1(x_res)
-  const void* xr = x_res;
-  if (bf16 || h->conv1.Cin_p != D) {
-    if ((rc = btc_pad_cast(bf.xr, h->act_dt, x_res, rows, D, h->conv1.Cin_p, st))) return rc;
-    xr = bf.xr;
-  }
-  if ((rc = run_dense(h, h->conv1, xr, bf.x, BVG_F32, nullptr, nullptr, B, T, st))) return rc;
+  if ((rc = run_dense(h, h->conv1, bf.xr, bf.x, BVG_F32, nullptr, nullptr, B, T, st))) return rc;
   if (bf16) wn_prepare_kernel<__nv_bfloat16><<<ew_blocks(rows * H), 256, 0, st>>>((__nv_bfloat16*)bf.xp, bf.skip, bf.x, B, T, H, P);
   else wn_prepare_kernel<float><<<ew_blocks(rows * H), 256, 0, st>>>((float*)bf.xp, bf.skip, bf.x, B, T, H, P);
   BVG_LAUNCHED();
@@ -531,13 +522,13 @@ extern "C" int bvg_s2mel_tail_fwd(bvg_s2mel_tail* h, const float* x_res, const i
     BVG_LAUNCHED();
     if ((rc = run_dense(h, h->res_skip[i], bf.acts, bf.rs, BVG_F32, nullptr, nullptr, B, T, st))) return rc;
     const int last = i == L - 1;
-    if (bf16) wn_update_kernel<__nv_bfloat16><<<ew_blocks(rows * H), 256, 0, st>>>(bf.x, (__nv_bfloat16*)bf.xp, bf.skip, bf.rs, x_lens, B, T, H, P, last);
-    else wn_update_kernel<float><<<ew_blocks(rows * H), 256, 0, st>>>(bf.x, (float*)bf.xp, bf.skip, bf.rs, x_lens, B, T, H, P, last);
+    if (bf16) wn_update_kernel<__nv_bfloat16><<<ew_blocks(rows * H), 256, 0, st>>>(bf.x, (__nv_bfloat16*)bf.xp, bf.skip, bf.rs, lens, B, T, H, P, last);
+    else wn_update_kernel<float><<<ew_blocks(rows * H), 256, 0, st>>>(bf.x, (float*)bf.xp, bf.skip, bf.rs, lens, B, T, H, P, last);
     BVG_LAUNCHED();
   }
   // y = wavenet(...)^T + res_projection(x_res)   (the skip sum rides in as the conv's residual operand)
-  if ((rc = run_dense(h, h->res_proj, xr, bf.y, BVG_F32, bf.skip, nullptr, B, T, st))) return rc;
-  // final_layer: LayerNorm -> modulate -> Linear;  conv2;  [B, T, C] -> [B, C, T]
+  if ((rc = run_dense(h, h->res_proj, bf.xr, bf.y, BVG_F32, bf.skip, nullptr, B, T, st))) return rc;
+  // final_layer: LayerNorm -> modulate -> Linear;  conv2
   {
     const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
     if (bf16) ln_modulate_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)bf.yb, bf.y, bf.mod, rows, T, H, 1e-6f);
@@ -545,9 +536,93 @@ extern "C" int bvg_s2mel_tail_fwd(bvg_s2mel_tail* h, const float* x_res, const i
     BVG_LAUNCHED();
   }
   if ((rc = run_dense(h, h->fin_linear, bf.yb, bf.hb, h->act_dt, nullptr, nullptr, B, T, st))) return rc;
-  if ((rc = run_dense(h, h->conv2, bf.hb, bf.o, BVG_F32, nullptr, nullptr, B, T, st))) return rc;
-  return btc_to_bct(out, bf.o, BVG_F32, B, h->cfg.out_channels, h->conv2.Cout_n, T, st);
+  return run_dense(h, h->conv2, bf.hb, bf.o, BVG_F32, nullptr, nullptr, B, T, st);
 }
+
+static void drop_tail_graphs(bvg_s2mel_tail* h) {
+  if (h->graphs.empty()) return;
+  cudaDeviceSynchronize();                      // replays may still be in flight
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+  h->graphs.clear();
+}
+}  // namespace bvg
+
+extern "C" int bvg_s2mel_tail_fwd(bvg_s2mel_tail* h, const float* x_res, const int* x_lens, const float* t, const float* t1,
+                                  float* out, int B, int T, bvg_stream_t stream) {
+  if (!h || !h->finalized) BVG_FAIL(BVG_ESTATE, "s2mel tail handle is not finalized");
+  if (B < 0 || T < 0) BVG_FAIL(BVG_EINVAL, "negative batch or length");
+  if (B == 0 || T == 0) return BVG_OK;
+  if (!x_res || !t || !t1 || !out) BVG_FAIL(BVG_EINVAL, "null pointer");
+  if (T <= h->P) BVG_FAIL(BVG_EINVAL, "T = %d: reflect padding of the k = %d in_layers needs T > %d", T, h->cfg.kernel_size, h->P);
+  BVG_DEVICE(h->cfg.device);
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->cfg.hidden, D = h->cfg.dit_hidden;
+  {
+    const size_t need = plan_tail(h, nullptr, B, T).total;
+    if (need > h->arena_bytes) {
+      drop_tail_graphs(h);                      // graphs bake arena addresses
+      if (h->arena) { BVG_CUDA(cudaDeviceSynchronize()); cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; }
+      BVG_CUDA(cudaMalloc((void**)&h->arena, need));
+      h->arena_bytes = need;
+    }
+  }
+  const TailBufs bf = plan_tail(h, h->arena, B, T);
+  const uint64_t l0 = g_launches.load();
+  // stage the caller's tensors into the arena (the only accesses to caller memory besides the final transpose)
+  BVG_CUDA(cudaMemcpyAsync(bf.t_in, t, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  BVG_CUDA(cudaMemcpyAsync(bf.t1_in, t1, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, st));
+  if (x_lens) BVG_CUDA(cudaMemcpyAsync(bf.lens_in, x_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if ((rc = btc_pad_cast(bf.xr, h->act_dt, x_res, (int64_t)B * T, D, h->conv1.Cin_p, st))) return rc;
+
+  const auto key = std::make_tuple(B, T, x_lens ? 1 : 0);
+  bool use_graph = h->opt_graph == 1;
+  if (h->opt_graph == 2) {
+    if (h->seen.size() > 4096) h->seen.clear();
+    use_graph = h->seen[key]++ >= 1;            // from the SECOND forward of a shape on (the solver calls 25 times per utterance)
+  }
+  if (use_graph) {
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+      if (h->graphs.size() >= 32) drop_tail_graphs(h);
+      cudaGraph_t g = nullptr;
+      cudaStream_t cs;
+      BVG_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      BVG_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const uint64_t k0 = g_launches.load();
+      rc = tail_body(h, bf, B, T, x_lens != nullptr, cs);
+      const int nkern = (int)(g_launches.load() - k0);
+      g_launches.store(k0);                     // captured, not launched
+      cudaError_t e = cudaStreamEndCapture(cs, &g);
+      cudaStreamDestroy(cs);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      BVG_CUDA(e);
+      cudaGraphExec_t ge = nullptr;
+      BVG_CUDA(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      it = h->graphs.emplace(key, std::make_pair(ge, nkern)).first;
+    }
+    BVG_CUDA(cudaGraphLaunch(it->second.first, st));
+    g_launches.fetch_add((uint64_t)it->second.second);
+  } else if ((rc = tail_body(h, bf, B, T, x_lens != nullptr, st))) {
+    return rc;
+  }
+  // [B, T, C] -> [B, C, T]
+  rc = btc_to_bct(out, bf.o, BVG_F32, B, h->cfg.out_channels, h->conv2.Cout_n, T, st);
+  h->last_launches = (int)(g_launches.load() - l0);
+  return rc;
+}
+
+extern "C" int bvg_s2mel_tail_set_option(bvg_s2mel_tail* h, const char* key, int value) {
+  if (!h || !key) BVG_FAIL(BVG_EINVAL, "bvg_s2mel_tail_set_option: null argument");
+  BVG_DEVICE(h->cfg.device);
+  if (!strcmp(key, "graph")) { h->opt_graph = value; return BVG_OK; }
+  if (!strcmp(key, "conv_own_sm")) { if (h->own_sm != value) drop_tail_graphs(h); h->own_sm = value; return BVG_OK; }
+  BVG_FAIL(BVG_EINVAL, "bvg_s2mel_tail_set_option: unknown option '%s'", key);
+}
+
+extern "C" int bvg_s2mel_tail_last_forward_launches(const bvg_s2mel_tail* h) { return h ? h->last_launches : 0; }
 
 extern "C" int bvg_cfm_euler_step(float* x, const float* dphi, float dt, double cfg_rate, int B, int C, int64_t T, int64_t prompt_len,
                                   bvg_stream_t stream) {

@@ -79,6 +79,17 @@ class S2MelTail(nn.Module):
         self.res_projection = nn.Linear(D, H)
         self._handle = None
         self._device = None
+        self._options = {}
+
+    def set_option(self, key, value):
+        """native options ("graph": 0 / 1 / 2, "conv_own_sm"); kept across rebuilds of the native handle"""
+        self._options[key] = int(value)
+        if self._handle is not None:
+            with torch.cuda.device(self._device):
+                _lib.check(_lib.load().bvg_s2mel_tail_set_option(self._handle, key.encode(), int(value)), "bvg_s2mel_tail_set_option")
+
+    def last_forward_launches(self):
+        return int(_lib.load().bvg_s2mel_tail_last_forward_launches(self._handle)) if self._handle is not None else 0
 
     # ---- weights ----------------------------------------------------------------------------------------------
     def folded_state_dict(self):
@@ -147,6 +158,8 @@ class S2MelTail(nn.Module):
                     _lib.check(lib.bvg_s2mel_tail_set_tensor(handle, n.encode(), t.data_ptr(), t.numel(), 1),
                                "bvg_s2mel_tail_set_tensor(%s)" % n)
             _lib.check(lib.bvg_s2mel_tail_finalize(handle), "bvg_s2mel_tail_finalize")
+            for k, v in self._options.items():
+                _lib.check(lib.bvg_s2mel_tail_set_option(handle, k.encode(), v), "bvg_s2mel_tail_set_option")
         except Exception:
             lib.bvg_s2mel_tail_destroy(handle)
             raise
