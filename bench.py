@@ -666,10 +666,98 @@ def main():
                 out["activation_sweep"] = rows
         except Exception as e:
             out["activation_sweep_summary"] = {"error": str(e)[:200]}
+    if rank == 0 and world == 1 and extras:
+        try:      # the next row of SURVEY section 8(f) built to the same bar: the s2mel tail in front of the vocoder
+            out["s2mel_tail"] = s2mel_tail_bench(cpu=not args.no_cpu_baseline, dev=dev)
+        except Exception as e:
+            out["s2mel_tail"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def s2mel_tail_bench(T=1863, B=2, cpu=True, dev="cuda:0"):
+    """`bvg_s2mel_tail_fwd` at the shape one solver step of infer_v2 runs (flow_matching.py:88-98:
+    the CFG-stacked batch of 2; 795 prompt + 1068 target frames as in the docstring of flow_matching.py:36), both precision
+    modes, the fused Euler / CFG update, and - as this path's cpu_baseline leg - the reference's operator sequence (oracle
+    restatement, <= 7e-7 from the unmodified DiT.forward) on torch CPU with all host threads, same shape."""
+    import statistics
+    import torch
+    tm = importlib.import_module("voice-tts_b200.s2mel_tail")
+    synth = importlib.import_module("voice-tts_b200.synth")
+    cfgm = importlib.import_module("voice-tts_b200.config")
+    _lib = importlib.import_module("voice-tts_b200._lib")
+    c = cfgm.s2mel_tail_config()
+    H, D, L, k, C = c["hidden"], c["dit_hidden"], c["n_layers"], c["kernel_size"], c["out_channels"]
+    macs_row = D * H + L * (H * 2 * H * k) + (L - 1) * (H * 2 * H) + H * H + D * H + H * H + H * C
+    flops = 2.0 * macs_row * B * T
+    sd = synth.make_s2mel_tail_state_dict(c, seed=1)
+    x_res, tt, t1, lens = synth.make_s2mel_tail_inputs(c, B, T)
+    out = {"workload": "s2mel tail (conv1 + WN x%d + res_projection + FinalLayer + conv2), %d x %d frames, random-init weights" % (L, B, T),
+           "gflop_per_call": flops / 1e9}
+    xr, td, t1d, ld = x_res.to(dev), tt.to(dev), t1.to(dev), lens.to(dev)
+    outs = {}
+
+    def timed(m, n=20, reps=5):
+        ts = []
+        with torch.no_grad():
+            for _ in range(3):
+                y = m(xr, ld, td, t1d)
+            for _ in range(reps):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    y = m(xr, ld, td, t1d)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) / n)
+        return statistics.median(ts), y
+
+    for prec in ("bf16", "fp32"):
+        m = tm.S2MelTail(c, precision=prec)
+        m.load_folded_state_dict(sd)
+        m = m.to(dev).eval()
+        ms, y = timed(m)
+        launches = m.last_forward_launches()
+        m.set_option("graph", 0)
+        eager_ms, y2 = timed(m, reps=1)
+        out[prec] = {"ms_per_call": ms, "ms_per_call_without_graph_replay": eager_ms, "tflops": flops / (ms * 1e-3) / 1e12,
+                     "launches": int(launches), "frames_per_s": B * T / (ms * 1e-3), "replay_bit_identical": bool(torch.equal(y, y2))}
+        outs[prec] = y.cpu()
+        del m
+    ref = outs["fp32"].double()
+    err = outs["bf16"].double() - ref
+    out["bf16"]["snr_db_vs_fp32_mode"] = float(10 * torch.log10(ref.pow(2).sum() / err.pow(2).sum()))
+    # one solver step's Euler / CFG update: x [1, 80, T], stacked estimator output [2, 80, T]
+    x = torch.randn(1, C, T, device=dev)
+    d = torch.randn(2, C, T, device=dev)
+    for _ in range(3):
+        tm.euler_step_(x, d, 0.04, 0.7, 100)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        tm.euler_step_(x, d, 0.04, 0.7, 100)
+    e1.record()
+    torch.cuda.synchronize()
+    out["euler_step_us"] = e0.elapsed_time(e1) / 200 * 1e3
+    if cpu:
+        from oracle import s2mel_oracle as S      # cpu_baseline leg: the checker, timed as the CPU arm of this path
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            S.tail_forward(sd, c, x_res, lens, tt, t1)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                yo = S.tail_forward(sd, c, x_res, lens, tt, t1)
+                ts.append(time.perf_counter() - t0)
+        out["cpu_baseline"] = {"ms_per_call": statistics.median(ts) * 1e3, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "the same %d x %d frames, median of 3 after 1 warm-up" % (B, T),
+                               "max_abs_diff_fp32_mode": float((outs["fp32"] - yo).abs().max())}
+        out["speedup_bf16_vs_cpu"] = out["cpu_baseline"]["ms_per_call"] / out["bf16"]["ms_per_call"]
+    return out
 
 
 def model_workspace_gb(model, B, T0):
