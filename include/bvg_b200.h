@@ -208,7 +208,8 @@ int bvg_vocoder_fwd_host(bvg_vocoder* v, const float* mel_host, void* wav_host, 
  * layer), "streams" (3 [default]: the AMP blocks of a stage on separate internal streams that fork from and join the caller's
  * stream; 1: serial; the result is bit-identical either way), "conv_own_sm" (1 [default]: the persistent tcgen05 conv kernels request the whole shared-memory carve-out of their SM;
  * 0: they leave room for one shared-memory-free block of another stream beside them), "pdl" (1: programmatic dependent launch of the
- * conv / activation kernels; 0 [default]: measured no gain).  Options that change what a forward enqueues drop captured graphs. */
+ * conv / activation kernels; 0 [default]: measured no gain), "fold" (1 [default]: resblock convolutions of <= 64-channel stages run
+ * as time-folded F*C-channel layers over the same tensors viewed as [T/F, F*C] where that saves tensor-core instructions; 0: off).  Options that change what a forward enqueues drop captured graphs. */
 int bvg_set_option(bvg_vocoder* v, const char* key, int value);
 /* per-kernel CUDA-event timing (set option "profile"=1 first; disables graph replay while on):
  * category 0 = tcgen05 conv, 1 = SIMT conv, 2 = fused activation, 3 = other, 4 = whole AMP unit in one kernel

@@ -30,6 +30,12 @@ struct ConvW {
   int Cin = 0, Cout = 0, Cin_p = 0, Cout_p = 0, Cout_n = 0, Cout_r = 0;
   int k = 0, k_torch = 0, dil = 1, up = 0;  // up > 0: ConvTranspose1d with stride `up`
   bool has_w = false, has_b = false, want_b = true;
+  // Time folding of narrow layers (bf16 mode, see build_fold_twin): a Conv1d over [T, Cp] with Cp <= 64 is the SAME memory as
+  // [T / F, F * Cp] and the same arithmetic as a conv with kf taps over F * Cp "phase channels" - the MMA tile (M = 128) then
+  // holds F time phases instead of F replicas of the layer.  The twin carries the re-packed weights / bias.
+  std::vector<float> w_host, b_host;  // torch-layout fp32 copies, kept only for layers that may fold
+  ConvW* fold_twin = nullptr;
+  int fold = 1;
 };
 
 // 1x1 conv on the speaker embedding (models.py:204-209): weight [C][E] fp32, bias [C]
@@ -82,6 +88,7 @@ struct bvg_vocoder {
   int fuse_res_min_kc = 4096;      // smallest k * Cin whose conv2 takes the fused residual + activation epilogue
   int opt_fuse_unit = 0;           // 1: whole AMP units of <= 96-channel stages as one kernel (amp_unit.cu; bf16 mode) - measured slower
                                    // than the layer-by-layer path on B200, so off by default
+  int opt_fold = 1;                // narrow resblock convolutions as time-folded F * Cp-channel layers where that saves MMAs
   int opt_pdl = 0;                 // programmatic dependent launch of the conv / activation kernels (common.cuh): bit-identical,
                                    // measured no gain (16 x 10 s: 39.8 vs 39.6 ms; 1 x 2 s: 1.44 vs 1.35 ms) - off by default
   int opt_streams = 3;             // AMP blocks of one stage run on up to this many streams (1 = serial); see DESIGN.md 8.5
@@ -323,6 +330,16 @@ static int run_conv(bvg_vocoder* v, const ConvW& c, const void* in, int in_dt, v
   a.in_dtype = in_dt; a.w_dtype = v->act_dt; a.out_dtype = out_dt;
   a.B = B; a.T = T; a.Cin_p = c.Cin_p; a.Cout_n = c.Cout_n; a.Cout_r = c.Cout_r; a.out_ld = c.Cout_n;
   a.k = c.k; a.dil = c.dil; a.own_sm = v->opt_own_sm;
+  if (c.fold_twin && v->opt_fold && v->cfg.mode == BVG_MODE_BF16 && v->opt_conv_impl != 1 && in_dt == BVG_BF16 && !bias_rows &&
+      T % c.fold == 0) {
+    // the same tensors viewed as [T / F, F * Cp], the layer as its time-folded twin (ConvW::fold_twin); flops reported below
+    // stay the layer's algorithmic ones
+    const ConvW& f = *c.fold_twin;
+    ConvArgs b = a;
+    b.w = f.w; b.bias = f.bias; b.T = T / c.fold;
+    b.Cin_p = f.Cin_p; b.Cout_n = f.Cout_n; b.Cout_r = f.Cout_r; b.out_ld = f.Cout_n; b.k = f.k; b.dil = 1;
+    if (conv_umma_supported(b)) a = b;
+  }
   if (v->cfg.mode == BVG_MODE_FP32 && v->opt_conv_impl == 3 && in_dt == BVG_F32 && sp && t && c.ws[0]) {
     void* const spl[3] = {sp[0], sp[1], sp[2]};
     SplitPlan pl;
@@ -684,6 +701,77 @@ static bool eat(const char*& s, const char* lit) {
   return true;
 }
 
+// ---- time folding of narrow resblock convolutions -----------------------------------------------------------------
+// out[t][co] = sum_j sum_ci W[co][ci][j] x[t + (j - c) d][ci]   with t = F t' + po and input row F (t' + tau) + pi:
+//   F tau + pi - po = (j - c) d   =>   Wf[tau][(po, co)][(pi, ci)] = W[co][ci][c + (F tau + pi - po) / d]   (0 where undefined)
+// a conv with kf = 2 floor((c d + F - 1) / F) + 1 taps, dilation 1, over F * Cp channels and T / F rows of the SAME tensors
+// (channels-last [T, Cp] is [T / F, F Cp]; pad channels stay pad channels; zero fill outside [0, T / F) is the layer's own
+// zero padding).  tcgen05 pays per K = 16 step whatever M holds, so the fold pays when kf * F Cp / 16 is well under
+// k * F * ceil(Cp / 16): 24 channels k = 11: 40 MMAs per 1 024 samples instead of 88, k = 7: 24 instead of 56.
+static int fold_factor(const bvg_vocoder* v, const ConvW& c) {
+  if (v->act_dt != BVG_BF16 || c.up > 0 || c.Cin_p != c.Cout_p || c.Cin_p > 64 || c.Cout_n != c.Cout_p) return 1;
+  const int F = 128 / c.Cin_p;
+  if (F < 2 || (F * c.Cin_p) % 16) return 1;
+  const int S = (c.k - 1) / 2 * c.dil, kf = 2 * ((S + F - 1) / F) + 1;
+  const int mm_plain = c.k * (int)ceil_div(c.Cin_p, 16) * F, mm_fold = kf * (F * c.Cin_p / 16);
+  return mm_fold * 10 <= mm_plain * 8 ? F : 1;
+}
+
+static void free_fold_twin(ConvW& c) {
+  if (!c.fold_twin) return;
+  if (c.fold_twin->w) cudaFree(c.fold_twin->w);
+  if (c.fold_twin->bias) cudaFree(c.fold_twin->bias);
+  delete c.fold_twin;
+  c.fold_twin = nullptr;
+  c.fold = 1;
+}
+
+static int build_fold_twin(bvg_vocoder* v, ConvW& c) {
+  free_fold_twin(c);
+  const int F = fold_factor(v, c);
+  if (F <= 1 || c.w_host.empty()) return BVG_OK;
+  const int Cp = c.Cin_p, Cf = F * Cp, cen = (c.k - 1) / 2, S = cen * c.dil;
+  const int kf = 2 * ((S + F - 1) / F) + 1, cf = (kf - 1) / 2;
+  std::vector<float> wf((size_t)Cf * Cf * kf, 0.f), bf((size_t)Cf, 0.f);
+  for (int po = 0; po < F; ++po)
+    for (int pi = 0; pi < F; ++pi)
+      for (int tau = -cf; tau <= cf; ++tau) {
+        const int delta = F * tau + pi - po;
+        if (delta % c.dil) continue;
+        const int j = cen + delta / c.dil;
+        if (j < 0 || j >= c.k) continue;
+        for (int co = 0; co < c.Cout; ++co)
+          for (int ci = 0; ci < c.Cin; ++ci)
+            wf[((size_t)(po * Cp + co) * Cf + (pi * Cp + ci)) * kf + (tau + cf)] = c.w_host[((size_t)co * c.Cin + ci) * c.k + j];
+      }
+  if (!c.b_host.empty())
+    for (int po = 0; po < F; ++po)
+      for (int co = 0; co < c.Cout; ++co) bf[(size_t)po * Cp + co] = c.b_host[co];
+  ConvW* t = new (std::nothrow) ConvW();
+  if (!t) BVG_FAIL(BVG_ENOMEM, "out of host memory");
+  t->Cin = t->Cout = Cf; t->Cin_p = t->Cout_p = t->Cout_n = Cf; t->Cout_r = round_up(Cf, 128);
+  t->k = t->k_torch = kf; t->dil = 1; t->up = 0;
+  int rc = alloc_conv(*t, BVG_BF16);
+  float* tmp = nullptr;
+  if (!rc && cudaMalloc((void**)&tmp, wf.size() * sizeof(float)) != cudaSuccess) rc = BVG_ENOMEM;
+  if (!rc && cudaMemcpy(tmp, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) rc = BVG_ECUDA;
+  if (!rc) rc = pack_conv_weight(t->w, BVG_BF16, tmp, Cf, Cf, kf, t->Cout_r, Cf, 0);
+  if (!rc && cudaMemcpy(t->bias, bf.data(), bf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) rc = BVG_ECUDA;
+  if (cudaDeviceSynchronize() != cudaSuccess && !rc) rc = BVG_ECUDA;
+  if (tmp) cudaFree(tmp);
+  if (rc) {
+    if (t->w) cudaFree(t->w);
+    if (t->bias) cudaFree(t->bias);
+    delete t;
+    if (rc == BVG_ECUDA || rc == BVG_ENOMEM) set_error("building the time-folded twin of a %d-channel k = %d layer failed", c.Cin, c.k);
+    return rc;
+  }
+  t->has_w = t->has_b = true;
+  c.fold_twin = t;
+  c.fold = F;
+  return BVG_OK;
+}
+
 static int set_conv_tensor(bvg_vocoder* v, ConvW& c, bool is_weight, const float* d_data, int64_t numel,
                            const char* name) {
   if (is_weight) {
@@ -692,6 +780,10 @@ static int set_conv_tensor(bvg_vocoder* v, ConvW& c, bool is_weight, const float
     int rc = c.up > 0 ? pack_convtr_weight(c.w, v->act_dt, d_data, c.Cin, c.Cout, c.up, c.k_torch, c.Cout_p, c.Cout_r, c.Cin_p, 0)
                       : pack_conv_weight(c.w, v->act_dt, d_data, c.Cout, c.Cin, c.k, c.Cout_r, c.Cin_p, 0);
     if (rc) return rc;
+    if (fold_factor(v, c) > 1) {
+      c.w_host.resize((size_t)numel);
+      BVG_CUDA(cudaMemcpy(c.w_host.data(), d_data, (size_t)numel * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     if (c.ws[0]) {
       // fp32 mode: w = w0 + w1 + w2 (bf16 terms), each packed for the tcgen05 kernels (run_conv_split)
       float* tmp = nullptr;
@@ -715,8 +807,13 @@ static int set_conv_tensor(bvg_vocoder* v, ConvW& c, bool is_weight, const float
     } else {
       BVG_CUDA(cudaMemcpy(c.bias, d_data, c.Cout * sizeof(float), cudaMemcpyDeviceToDevice));
     }
+    if (fold_factor(v, c) > 1) {
+      c.b_host.resize((size_t)c.Cout);
+      BVG_CUDA(cudaMemcpy(c.b_host.data(), d_data, (size_t)c.Cout * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     c.has_b = true;
   }
+  if (v->finalized) return build_fold_twin(v, c);   // a weight replaced after bvg_finalize: the folded twin follows
   return BVG_OK;
 }
 
@@ -959,6 +1056,11 @@ int vocoder_finalize(bvg_vocoder* v) {
   }
   if (!v->has_post_w) BVG_FAIL(BVG_ESTATE, "missing weight: conv_post.weight");
   if (v->cfg.use_bias_at_final && !v->has_post_b) BVG_FAIL(BVG_ESTATE, "missing weight: conv_post.bias");
+  for (auto* group : {&v->convs1, &v->convs2})
+    for (auto& c : *group) {
+      const int rc = build_fold_twin(v, c);
+      if (rc) return rc;
+    }
   v->finalized = true;
   return BVG_OK;
 }
@@ -1020,6 +1122,7 @@ extern "C" void bvg_destroy(bvg_vocoder* v) {
   DeviceGuard dg(v->cfg.device);
   cudaDeviceSynchronize();
   auto free_conv = [](ConvW& c) {
+    free_fold_twin(c);
     if (c.w) cudaFree(c.w);
     if (c.bias) cudaFree(c.bias);
     for (int q = 0; q < 3; ++q) if (c.ws[q]) cudaFree(c.ws[q]);
@@ -1070,7 +1173,7 @@ extern "C" int bvg_set_option(bvg_vocoder* v, const char* key, int value) {
       {"fuse_res", &v->opt_fuse_res, true},     {"fuse_res_min_kc", &v->fuse_res_min_kc, true},
       {"fuse_act", &v->opt_fuse_act, true},     {"fuse_unit", &v->opt_fuse_unit, true},
       {"streams", &v->opt_streams, true},       {"conv_own_sm", &v->opt_own_sm, true},
-      {"pdl", &v->opt_pdl, true},
+      {"pdl", &v->opt_pdl, true},               {"fold", &v->opt_fold, true},
   };
   for (const Opt& o : opts) {
     if (strcmp(key, o.name)) continue;
