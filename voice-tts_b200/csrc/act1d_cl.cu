@@ -400,6 +400,9 @@ static int launch_cl(void* dst, const void* src, const float* alpha_log, const f
       break;
     }
   }
+  // one short utterance: the kernel's duration is a thread's serial walk (L + 5 steps), not its throughput - 7-row segments
+  // (12 steps for 7 outputs) halve it while the grid is still far from filling the machine
+  if (L == kSegLens[4] && (int64_t)B * ceil_div(T, kSegLens[4]) * P < want_items / 4) L = 7;
   // interior segments: kEdge + s*L + L + 4 + 12 (prefetch run-ahead) <= T - 1
   int64_t n_int = (T - 5 - 12 - kEdge) / L;
   if (n_int < 0) n_int = 0;

@@ -522,6 +522,10 @@ static bool ua_plan(const ConvArgs& a, UAParams& p) {
   p.w_resident = (ncot == 1 && a.k * p.nchunks <= p.a_stages) ? 1 : 0;
   p.S = p.rep == 1 ? 120 : (p.rep == 2 ? 60 : 24);
   p.Rs = p.rep == 4 ? 12 : 30;
+  // small problems (one short utterance): if the half-width tiles (N = 144 instead of 256: ~100 instead of ~150 cycles per
+  // tcgen05.mma, tools/umma_probe.cu) still fit one wave, every layer finishes sooner - a 768-channel k = 11 layer on one 2 s
+  // utterance is 18 tiles of 528 MMAs otherwise
+  if (p.rep == 1 && (int64_t)a.B * ceil_div(a.T, 120) * ncot <= umma_sm_count()) p.S = 60;
   p.NOUT = 2 * p.rep * p.S;
   p.NT = round_up(p.NOUT + 11, 16);
   if (p.NT + halo > UA_MAX_X_ROWS - 8) return false;
