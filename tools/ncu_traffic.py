@@ -11,7 +11,7 @@ per = collections.OrderedDict()
 for r in rows[1:]:
     d = dict(zip(hdr, r))
     per.setdefault((int(d["ID"]), d["Kernel Name"].split("(")[0].replace("void ", "").replace("bvg::", "")), {})[d["Metric Name"]] = \
-        float(d["Metric Value"].replace(",", "")) * U[d["Metric Unit"]]
+        float(d["Metric Value"].replace(",", "")) * U.get(d["Metric Unit"], 1)
 agg = collections.OrderedDict()
 cats = {"conv_tcgen05": [0, 0.0, 0.0, 0.0], "activation": [0, 0.0, 0.0, 0.0], "other": [0, 0.0, 0.0, 0.0]}
 for (_, name), m in per.items():
