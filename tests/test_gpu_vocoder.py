@@ -287,6 +287,30 @@ def test_full_generator_bf16_option_matrix(pkg, golden, full_model_sd, opts):
         assert torch.equal(wav, wav0)
 
 
+@pytest.mark.parametrize("which", ["full", "tiny", "tiny_k5_d2"])
+def test_time_folded_convs_match_unfolded(pkg, synth, cfg, golden, full_model_sd, which):
+    """Time folding (a Conv1d over [T, Cp <= 64] as its kf-tap twin over [T/F, F*Cp]) multiplies the same
+    operands and only re-orders the fp32 accumulation: with the fusion policy pinned (fuse_act = 0: the folding also changes
+    which layers fuse), fold = 1 and fold = 0 agree to accumulation noise (>= 70 dB; a misplaced tap would cost tens of dB),
+    on the full plan (24 / 48 channels: F = 4 / 2), the tiny plan (12 channels padded to 16: F = 8) and a plan with even dilation."""
+    if which == "full":
+        h, sd = full_model_sd
+        mel = t(golden("generators")["full.mel"]).to(DEV)
+    else:
+        h = cfg.tiny_hparams() if which == "tiny" else cfg.tiny_hparams(resblock_kernel_sizes=[5, 7, 11],
+                                                                          resblock_dilation_sizes=[[1, 2, 4]] * 3)
+        sd = synth.make_state_dict(h, seed=11)
+        mel = synth.make_mel(2, h["num_mels"], 52).to(DEV)
+    folded = make(pkg, h, sd, "bf16", fuse_act=0, fuse_res=0)
+    plain = make(pkg, h, sd, "bf16", fuse_act=0, fuse_res=0, fold=0)
+    with torch.no_grad():
+        a, b = folded(mel).cpu(), plain(mel).cpu()
+    snr = O.snr_db(b, a)
+    print("time folding %s: folded vs unfolded %.1f dB" % (which, snr))
+    assert snr >= 70.0
+    assert not torch.equal(a, b), "fold = 1 did not change the plan: no layer folded?"
+
+
 def test_multi_stream_soak(pkg, synth, full_model_sd):
     """Soak of the default schedule: the three AMP blocks of a stage on three streams, with and without
     CUDA-graph replay - 300 forwards each, every one bit-identical to the serial schedule - and the same with CTAs of other
