@@ -116,6 +116,8 @@ struct bvg_vocoder {
   std::map<std::pair<int, int>, int> shape_seen;                          // forwards per (B, T0) so far (graph = 2)
 };
 
+static int drop_graphs(bvg_vocoder* v);   // defined with bvg_set_option below
+
 namespace bvg {
 
 static int dev_alloc(void** p, size_t bytes) {
@@ -717,6 +719,8 @@ static int fold_factor(const bvg_vocoder* v, const ConvW& c) {
   if (F < 2 || (F * c.Cin_p) % 16) return 1;
   const int S = (c.k - 1) / 2 * c.dil, kf = 2 * ((S + F - 1) / F) + 1;
   const int mm_plain = c.k * (int)ceil_div(c.Cin_p, 16) * F, mm_fold = kf * (F * c.Cin_p / 16);
+  // (folding at EQUAL MMA counts - k = 3, or k = 7 with dilation 3 at 24 channels - was measured too: 0.03-0.05 ms per launch on four
+  //  launches, nothing on the step)
   return mm_fold * 10 <= mm_plain * 8 ? F : 1;
 }
 
@@ -816,7 +820,11 @@ static int set_conv_tensor(bvg_vocoder* v, ConvW& c, bool is_weight, const float
     }
     c.has_b = true;
   }
-  if (v->finalized) return build_fold_twin(v, c);   // a weight replaced after bvg_finalize: the folded twin follows
+  if (v->finalized && fold_factor(v, c) > 1) {
+    // a weight replaced after bvg_finalize: the folded twin follows; captured graphs hold the old twin's addresses
+    const int rc = ::drop_graphs(v);
+    return rc ? rc : build_fold_twin(v, c);
+  }
   return BVG_OK;
 }
 
