@@ -195,3 +195,42 @@ def test_bench_arms_share_config_and_metric():
             for T, f in ((8192, 0.3), (131072, 0.4), (2097152, 0.5))]
     s = bench.act_sweep_summary(rows, {"hbm_gbs": 6547.8})["series"]["ours bfloat16 fast"]
     assert s["frac_min"] == 0.3 and s["frac_max"] == 0.5 and s["frac_median"] == 0.4 and s["frac_median_T_ge_131072"] == 0.5
+
+
+@pytest.mark.parametrize("C,k,d,F", [(24, 11, 1, 4), (24, 7, 1, 4), (48, 11, 1, 2), (12, 7, 1, 8), (24, 11, 3, 4), (16, 5, 2, 8)])
+def test_time_folding_identity(C, k, d, F):
+    """The identity behind `vocoder.cu: build_fold_twin`: a zero-padded Conv1d over [T, C] equals a
+    dilation-1 conv with kf = 2*floor((c*d + F - 1)/F) + 1 taps over the same memory viewed as [T/F, F*C], with
+    Wf[tau][(po,co)][(pi,ci)] = W[co][ci][c + (F*tau + pi - po)/d] (0 where undefined).  Checked in float64 on the CPU."""
+    import numpy as np
+    rng = np.random.default_rng(C * 100 + k * 10 + d)
+    T = 8 * F * 3
+    W = rng.standard_normal((C, C, k))
+    x = rng.standard_normal((T, C))
+    cen = (k - 1) // 2
+    S = cen * d
+    y = np.zeros((T, C))
+    for t in range(T):
+        for j in range(k):
+            tt = t + (j - cen) * d
+            if 0 <= tt < T:
+                y[t] += W[:, :, j] @ x[tt]
+    kf = 2 * ((S + F - 1) // F) + 1
+    cf = (kf - 1) // 2
+    Wf = np.zeros((kf, F * C, F * C))
+    for po in range(F):
+        for pi in range(F):
+            for tau in range(-cf, cf + 1):
+                delta = F * tau + pi - po
+                if delta % d:
+                    continue
+                j = cen + delta // d
+                if 0 <= j < k:
+                    Wf[tau + cf, po * C:(po + 1) * C, pi * C:(pi + 1) * C] = W[:, :, j]
+    xf = x.reshape(T // F, F * C)
+    yf = np.zeros((T // F, F * C))
+    for t in range(T // F):
+        for tau in range(-cf, cf + 1):
+            if 0 <= t + tau < T // F:
+                yf[t] += Wf[tau + cf] @ xf[t + tau]
+    assert np.allclose(yf.reshape(T, C), y, rtol=1e-12, atol=1e-12)
