@@ -106,6 +106,35 @@ def test_tail_graph_replay_is_bit_identical(tail_mod, synth, cfg):
     assert graphed.last_forward_launches() == eager.last_forward_launches() > 20
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_tail_fuzz_vs_oracle(tail_mod, synth, cfg, seed):
+    """seeded random configurations (widths off the 64-channel tile grid, 1-4 layers, k = 3 / 5 / 7, ragged lengths incl.
+    length-1 and zero-length masks, T down to k // 2 + 1) against the oracle: fp32 mode <= 1e-5, bf16 mode >= 40 dB"""
+    import random
+    rnd = random.Random(1000 + seed)
+    H = rnd.choice([16, 32, 48, 80, 96, 128, 160])
+    k = rnd.choice([3, 5, 7])
+    c = cfg.s2mel_tail_config(hidden=H, dit_hidden=H, n_layers=rnd.randint(1, 4), kernel_size=k,
+                              out_channels=rnd.choice([8, 20, 80, 100]), freq_dim=rnd.choice([32, 256]))
+    B = rnd.randint(1, 3)
+    T = rnd.choice([k // 2 + 1, k, 9, 17, 40, 63, 90])
+    lens = [rnd.choice([0, 1, T // 2, T]) for _ in range(B)]
+    lens[rnd.randrange(B)] = T
+    sd = synth.make_s2mel_tail_state_dict(c, seed=seed)
+    x_res, tt, t1, x_lens = synth.make_s2mel_tail_inputs(c, B, T, seed=seed, lens=lens)
+    ref = S.tail_forward(sd, c, x_res, x_lens, tt, t1)
+    for precision in ("fp32", "bf16"):
+        m = tail_mod.S2MelTail(c, precision=precision)
+        m.load_folded_state_dict(sd)
+        m = m.to(DEV).eval()
+        with torch.no_grad():
+            y = m(x_res.to(DEV), x_lens.to(DEV), tt.to(DEV), t1.to(DEV)).cpu()
+        if precision == "fp32":
+            assert float((y - ref).abs().max() / ref.abs().max()) <= 1e-5, (c, B, T, lens)
+        else:
+            assert O.snr_db(ref, y) >= 40.0, (c, B, T, lens, O.snr_db(ref, y))
+
+
 def test_tail_rejects_bad_arguments(tail_mod, synth, cfg):
     c = cfg.s2mel_tail_config(hidden=32, dit_hidden=32, n_layers=2)
     m = make(tail_mod, synth, c, 1, "fp32")
