@@ -528,10 +528,15 @@ def main():
             t_ref_form = timed(loop_reference_form)
             t_i16 = timed(loop_host_int16)
             t_batched = timed(lambda: [w.cpu() for w in model.forward_segments(segs)])
+            t_serial = timed(lambda: [w.cpu() for w in model.forward_segments(segs, concurrency=1)])
+            t_three = timed(lambda: [w.cpu() for w in model.forward_segments(segs, concurrency=3)])
             replay = {"segments": len(seg_frames), "frames": seg_frames, "audio_s": audio,
                       "loop_as_infer_v2": {"bigvgan_time_s": t_ref_form, "rtf": t_ref_form / audio, "x_realtime": audio / t_ref_form},
                       "loop_forward_host_int16": {"bigvgan_time_s": t_i16, "rtf": t_i16 / audio, "x_realtime": audio / t_i16},
-                      "forward_segments_one_call": {"bigvgan_time_s": t_batched, "rtf": t_batched / audio, "x_realtime": audio / t_batched},
+                      "forward_segments_one_call": {"bigvgan_time_s": t_batched, "rtf": t_batched / audio, "x_realtime": audio / t_batched,
+                                                    "concurrency": 2},
+                      "forward_segments_serial": {"bigvgan_time_s": t_serial, "x_realtime": audio / t_serial, "concurrency": 1},
+                      "forward_segments_3_workers": {"bigvgan_time_s": t_three, "x_realtime": audio / t_three, "concurrency": 3},
                       "note": "vocoder stage only (GPT + s2mel out of scope); median of 5 wall-clock passes after 2 warm-ups"}
 
     value = audio_s_step * args.steps / (ms * 1e-3)

@@ -395,11 +395,14 @@ def test_forward_segments_ragged_batching(pkg, synth, full_model_sd):
     lengths = [57, 130, 57, 301, 130, 57, 12]
     mels = [synth.make_mel(1, 80, T, first_utterance=i)[0].to(DEV) for i, T in enumerate(lengths)]
     with torch.no_grad():
-        wavs = m.forward_segments(mels)
         singles = [m(x.unsqueeze(0))[0] for x in mels]
-    assert [tuple(w.shape) for w in wavs] == [(1, T * 256) for T in lengths]
-    for w, s in zip(wavs, singles):
-        assert torch.equal(w, s)
+        for conc in (1, 2, 3, 2):         # length groups on 1 / 2 / 3 native handles and streams (the second pass of 2 replays graphs)
+            wavs = m.forward_segments(mels, concurrency=conc)
+            torch.cuda.synchronize()
+            assert [tuple(w.shape) for w in wavs] == [(1, T * 256) for T in lengths]
+            for w, s in zip(wavs, singles):
+                assert torch.equal(w, s), conc
+        assert m.forward_segments([]) == [] and m.forward_segments([mels[0][:, :0]])[0].shape == (1, 0)
 
 
 @pytest.mark.parametrize("overrides", [

@@ -122,6 +122,8 @@ class BigVGAN(nn.Module):
         self.conv_post = weight_norm(Conv1d(ch, 1, 7, 1, padding=3, bias=self.use_bias_at_final))
         self.use_tanh_at_final = h.get("use_tanh_at_final", True)
         self._hid = None
+        self._worker_hids = []       # extra native handles of forward_segments (one per concurrent length group)
+        self._worker_streams = []
         self._options = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
@@ -130,6 +132,9 @@ class BigVGAN(nn.Module):
         if self._hid is not None:
             ops.release_handle(self._hid)
             self._hid = None
+        for hid in getattr(self, "_worker_hids", []):
+            ops.release_handle(hid)
+        self._worker_hids = []
 
     def _apply(self, fn, *args, **kwargs):
         self._invalidate()
@@ -144,8 +149,8 @@ class BigVGAN(nn.Module):
     def set_option(self, key, value):
         """native options: graph, conv_impl (0 auto / 1 simt / 2 tcgen05), fast_sin, workspace_mb"""
         self._options[key] = int(value)
-        if self._hid is not None:
-            _lib.check(_lib.load().bvg_set_option(ops._HANDLES[self._hid][0], key.encode(), int(value)), "bvg_set_option")
+        for hid in ([self._hid] if self._hid is not None else []) + list(self._worker_hids):
+            _lib.check(_lib.load().bvg_set_option(ops._HANDLES[hid][0], key.encode(), int(value)), "bvg_set_option")
 
     def folded_state_dict(self):
         """state dict with weight norm folded (the keys `remove_weight_norm()` leaves)."""
@@ -161,6 +166,9 @@ class BigVGAN(nn.Module):
         return sd
 
     def _build_native(self, device):
+        self._hid = self._make_handle(device)
+
+    def _make_handle(self, device):
         import ctypes
         h = self.h
         lib = _lib.load()
@@ -210,7 +218,7 @@ class BigVGAN(nn.Module):
         except Exception:
             lib.bvg_destroy(handle)
             raise
-        self._hid = ops.register_handle(handle, in_channels(h), total_upsample(h), cfg.device)
+        return ops.register_handle(handle, in_channels(h), total_upsample(h), cfg.device)
 
     def _native_conditioning(self):
         """(input_channels_last, cond_dim, cond_each_up) of the native plan; the v1 subclass overrides it."""
@@ -256,7 +264,7 @@ class BigVGAN(nn.Module):
         _lib.check(rc, "bvg_vocoder_fwd_host")
         return out
 
-    def forward_segments(self, mels):
+    def forward_segments(self, mels, concurrency=2):
         """Vocode a list of segments of DIFFERENT lengths in as few launches as exactness allows.
 
         `infer_v2.py:616-744` runs the vocoder once per text segment (`wav = self.bigvgan(vc_target.float())`).  Segments of
@@ -275,14 +283,51 @@ class BigVGAN(nn.Module):
         for i, m in enumerate(items):
             groups.setdefault(int(m.shape[-1]), []).append(i)
         out = [None] * len(items)
-        for T, idx in sorted(groups.items()):
-            if T == 0:
-                for i in idx:
-                    out[i] = items[i].new_empty(1, 0)
-                continue
-            wav = self.forward(torch.cat([items[i] for i in idx], dim=0).float())
-            for row, i in enumerate(idx):
-                out[i] = wav[row]
+        for i in groups.pop(0, []):
+            out[i] = items[i].new_empty(1, 0)
+        todo = sorted(groups.items(), key=lambda kv: -kv[0] * len(kv[1]))       # largest group first
+        workers = max(1, min(int(concurrency), len(todo)))
+        if workers == 1:
+            for T, idx in todo:
+                wav = self.forward(torch.cat([items[i] for i in idx], dim=0).float())
+                for row, i in enumerate(idx):
+                    out[i] = wav[row]
+            return out
+        # Different lengths cannot share a batch (see above) but they can share the GPU: a single 3-15 s segment leaves SMs idle
+        # in the wide stages.  Groups are dealt to `workers` native handles (own workspace, weights packed once per handle),
+        # each on its own stream that forks from and joins the caller's stream; per segment the kernels and their order are
+        # exactly those of `self(mel)`, so the results stay bit-identical.
+        dev = items[0].device
+        if self._hid is None or ops._HANDLES[self._hid][3] != dev.index:
+            self._invalidate()
+            self._build_native(dev)
+        while len(self._worker_hids) < workers - 1:
+            self._worker_hids.append(self._make_handle(dev))
+        if len(self._worker_streams) < workers - 1 or any(s.device != dev for s in self._worker_streams):
+            self._worker_streams = [torch.cuda.Stream(device=dev) for _ in range(workers - 1)]
+        load = [0] * workers
+        plan = [[] for _ in range(workers)]
+        for T, idx in todo:                                                      # longest-processing-time-first assignment
+            w = load.index(min(load))
+            plan[w].append((T, idx))
+            load[w] += T * len(idx)
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for w in range(workers):
+            stream = cur if w == 0 else self._worker_streams[w - 1]
+            hid = self._hid if w == 0 else self._worker_hids[w - 1]
+            with torch.cuda.stream(stream):
+                if w:
+                    stream.wait_event(fork)
+                for T, idx in plan[w]:
+                    wav = ops.vocoder(torch.cat([items[i] for i in idx], dim=0).float().contiguous(), hid)
+                    if w:
+                        wav.record_stream(cur)
+                    for row, i in enumerate(idx):
+                        out[i] = wav[row]
+        for w in range(1, workers):
+            cur.wait_stream(self._worker_streams[w - 1])
         return out
 
     def read_profile(self):
