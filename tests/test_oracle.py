@@ -244,3 +244,40 @@ def test_s2mel_tail_host_mirror_key_names(synth, cfg):
     assert set(back) == set(sd)
     for k in sd:
         assert torch.allclose(back[k], sd[k], rtol=1e-6, atol=1e-7), k
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_s2mel_tail_takes_the_reference_dit_state_dict(cfg):
+    """drop-in check against the REAL reference module: `S2MelTail.from_dit` reads its configuration off a reference DiT and
+    loads the tail's share of its state dict strictly (key names and shapes, weight_g / weight_v included); the folded weights
+    equal what the reference's weight-normed layers evaluate to, and the oracle on them reproduces DiT.forward"""
+    import importlib, sys, types
+    if "munch" not in sys.modules:
+        sys.modules["munch"] = types.ModuleType("munch")
+        sys.modules["munch"].Munch = dict
+    refshim.load()
+    from indextts.s2mel.modules import diffusion_transformer
+    from oracle.make_golden import s2mel_args
+    from oracle import s2mel_oracle as S
+    tm = importlib.import_module("voice-tts_b200.s2mel_tail")
+    c = cfg.s2mel_tail_config(hidden=64, dit_hidden=64, n_layers=3)
+    torch.manual_seed(3)
+    dit = diffusion_transformer.DiT(s2mel_args(c)).eval()
+    tail = tm.S2MelTail.from_dit(dit, precision="fp32")
+    assert tail.cfg == dict(c)
+    sd = tail.folded_state_dict()
+    assert torch.allclose(sd["wavenet.in_layers.1.weight"], dit.wavenet.in_layers[1].conv.conv.weight, atol=1e-7)
+    assert torch.allclose(sd["final_layer.linear.weight"], dit.final_layer.linear.weight, atol=1e-7)
+    B, T = 2, 23
+    dit.setup_caches(B, T)
+    cap = {}
+    dit.skip_linear.register_forward_hook(lambda m, i, o: cap.__setitem__("x_res", o.detach().clone()))
+    dit.t_embedder.register_forward_hook(lambda m, i, o: cap.__setitem__("t1", o.detach().clone()))
+    g = torch.Generator().manual_seed(5)
+    x_lens = torch.tensor([T, 11])
+    tt = torch.rand(B, generator=g)
+    with torch.no_grad():
+        y = dit(torch.randn(B, 80, T, generator=g), torch.randn(B, 80, T, generator=g), x_lens, tt,
+                torch.randn(B, 24, generator=g), torch.randn(B, T, 64, generator=g))
+        ours = S.tail_forward({k: v.detach() for k, v in sd.items()}, c, cap["x_res"], x_lens, tt, cap["t1"])
+    assert float((ours - y).abs().max() / y.abs().max()) <= 1e-5

@@ -81,6 +81,19 @@ class S2MelTail(nn.Module):
         self._device = None
         self._options = {}
 
+    @classmethod
+    def from_dit(cls, dit, precision="bf16"):
+        """Build the tail of a reference `DiT` instance (diffusion_transformer.py:101-175 with final_layer_type 'wavenet'):
+        configuration read off its sub-modules, weights loaded under its own state-dict keys, same device."""
+        w = dit.wavenet
+        k = w.kernel_size[0] if isinstance(w.kernel_size, (tuple, list)) else w.kernel_size   # wavenet.py:108 stores a 1-tuple
+        cfg = dict(hidden=w.hidden_channels, dit_hidden=dit.conv1.in_features, n_layers=w.n_layers, kernel_size=int(k),
+                   dilation_rate=w.dilation_rate, out_channels=dit.conv2.out_channels,
+                   freq_dim=dit.t_embedder2.frequency_embedding_size)
+        m = cls(cfg, precision=precision)
+        m.load_state_dict(tail_keys(dit.state_dict()), strict=True)
+        return m.to(dit.conv1.weight.device)
+
     def set_option(self, key, value):
         """native options ("graph": 0 / 1 / 2, "conv_own_sm"); kept across rebuilds of the native handle"""
         self._options[key] = int(value)
