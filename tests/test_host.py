@@ -52,6 +52,34 @@ def test_config_struct_matches_header(tmp_path):
     assert len(re.findall(r"^\s*int\s+\w+", body, re.M)) == len(names)      # every header field is mirrored
 
 
+def test_s2mel_config_struct_layout_matches_header(tmp_path):
+    """the ctypes mirror of bvg_s2mel_config has the header's size and field offsets (gcc), and the s2mel entry points fail
+    loudly without a device / on bad arguments (no CPU fallback)"""
+    import importlib
+    _lib = importlib.import_module("voice-tts_b200._lib")
+    names = [n for n, _ in _lib.S2MelConfig._fields_]
+    src = tmp_path / "sz2.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bvg_b200.h"\nint main(void){printf("%zu", sizeof(bvg_s2mel_config));'
+                   + "".join('printf(" %%zu", offsetof(bvg_s2mel_config, %s));' % n for n in names) + "return 0;}\n")
+    exe = tmp_path / "sz2"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert vals[0] == ctypes.sizeof(_lib.S2MelConfig)
+    assert vals[1:] == [getattr(_lib.S2MelConfig, n).offset for n in names]
+    lib = _lib.load()
+    c = _lib.S2MelConfig()
+    c.hidden, c.dit_hidden, c.n_layers, c.kernel_size, c.dilation_rate, c.out_channels, c.freq_dim, c.mode = 64, 64, 2, 4, 1, 80, 256, 1
+    h = ctypes.c_void_p()
+    assert lib.bvg_s2mel_tail_create(ctypes.byref(c), ctypes.byref(h)) == -1 and not h.value     # even kernel size: BVG_EINVAL
+    c.kernel_size, c.dilation_rate = 5, 2
+    assert lib.bvg_s2mel_tail_create(ctypes.byref(c), ctypes.byref(h)) == -1 and b"dilation_rate" in lib.bvg_last_error()
+    assert lib.bvg_cfm_euler_step(None, None, 0.1, 0.7, 1, 80, 0, 0, None) == 0                  # T == 0: no-op
+    assert lib.bvg_cfm_euler_step(None, None, 0.1, 0.7, 1, 80, 10, 0, None) == -1                # null pointers
+    if not torch.cuda.is_available():
+        c.dilation_rate = 1
+        assert lib.bvg_s2mel_tail_create(ctypes.byref(c), ctypes.byref(h)) in (-5, -4) and not h.value   # no device: no fallback
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
 def test_compute_entry_points_fail_loudly_without_gpu():
     import importlib
