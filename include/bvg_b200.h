@@ -27,6 +27,9 @@
  *                           indextts/infer.py:476,646 as `wav, _ = self.bigvgan(latent, auto_conditioning.transpose(1, 2))`
  *   bvg_vocoder_fwd_host <- the host round trip of indextts/infer_v2.py:735-744 (mel on host -> wav on host,
  *                           optional int16 quantisation `clamp(32767*wav)` of :740)
+ *   bvg_s2mel_tail_*     <- what DiT.forward does after its transformer, indextts/s2mel/modules/diffusion_transformer.py:245-256
+ *                           (conv1, WN of wavenet.py:103-164, res_projection, FinalLayer :82-99, conv2)
+ *   bvg_cfm_euler_step   <- the per-step arithmetic of BASECFM.solve_euler, indextts/s2mel/modules/flow_matching.py:103-112
  */
 #ifndef BVG_B200_H_
 #define BVG_B200_H_
