@@ -719,9 +719,9 @@ static int fold_factor(const bvg_vocoder* v, const ConvW& c) {
   if (F < 2 || (F * c.Cin_p) % 16) return 1;
   const int S = (c.k - 1) / 2 * c.dil, kf = 2 * ((S + F - 1) / F) + 1;
   const int mm_plain = c.k * (int)ceil_div(c.Cin_p, 16) * F, mm_fold = kf * (F * c.Cin_p / 16);
-  // (folding at EQUAL MMA counts - k = 3, or k = 7 with dilation 3 at 24 channels - was measured too: 0.03-0.05 ms per launch on four
-  //  launches, nothing on the step)
-  return mm_fold * 10 <= mm_plain * 8 ? F : 1;
+  // F = 4 (24 channels) also folds at EQUAL MMA counts - k = 3 with dilation 1 / 3, k = 7 with dilation 3: the folded tile moves
+  // 4x the bytes per TMA operation and per tile (measured 0.144 -> 0.110 and 0.202 -> 0.150 ms per launch); at F = 2 that gains nothing
+  return mm_fold * 10 <= mm_plain * (F >= 4 ? 10 : 8) ? F : 1;
 }
 
 static void free_fold_twin(ConvW& c) {
