@@ -20,7 +20,7 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, int row_bytes) {
   return d;
 }
 
-struct Case { int N, row_bytes, taps, dil, shift_a, rounds; };
+struct Case { int N, row_bytes, taps, dil, shift_a, rounds, M; };
 
 __global__ void __launch_bounds__(128, 1) probe(Case c, long long* out) {
   extern __shared__ unsigned char smem_dyn[];
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128, 1) probe(Case c, long long* out) {
   tc_fence_after();
   const uint32_t tm = slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(c.M >> 4) << 24);
     const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 96 * 1024);
     const uint64_t da0 = mk_desc(a_addr, c.row_bytes), db0 = mk_desc(b_addr, c.row_bytes);
     const int nkk = c.row_bytes / 32;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, 1) probe(Case c, long long* out) {
   if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
-int main() {
+int main(int argc, char** argv) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   long long* out;
@@ -73,6 +73,23 @@ int main() {
   std::vector<long long> h(sms * 2);
   const int smem = 200 * 1024;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (argc > 1 && argv[1][0] == 'm') {
+    // M = 64 against M = 128 (cta_group::1, 128-byte rows, no shift): does a half-height instruction cost less?
+    printf("%5s %5s | %11s %12s\n", "M", "N", "cyc/MMA avg", "MAC/clk/SM");
+    for (int M : {128, 64})
+      for (int N : {256, 192, 128, 64}) {
+        Case c{N, 128, 11, 0, 1, 9, M};
+        probe<<<sms, 128, smem>>>(c, out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error: %s (M=%d N=%d)\n", cudaGetErrorString(e), M, N); return 1; }
+        cudaMemcpy(h.data(), out, sms * 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long avg = 0;
+        for (int i = 0; i < sms; ++i) avg += h[2 * i + 1];
+        const double cavg = (double)avg / sms / (8 * 11 * 4);
+        printf("%5d %5d | %11.1f %12.0f\n", M, N, cavg, (double)M * N * 16 / cavg);
+      }
+    return 0;
+  }
   printf("%5s %9s %5s %4s %7s | %10s %10s %12s %10s\n", "N", "row_bytes", "taps", "dil", "shifted", "cyc/MMA min", "cyc/MMA avg", "MAC/clk/SM", "smemB/clk");
   const int Ns[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const int RBs[] = {128, 64, 32};
@@ -81,7 +98,7 @@ int main() {
       for (int N : Ns)
         for (int dil : {0, 1, 3, 4, 5, 8}) {
           if (shift_a == 0 && N != 256 && N != 128) continue;   // B-shift (channel-major) only for wide time tiles
-          Case c{N, rb, 11, dil, shift_a, 9};
+          Case c{N, rb, 11, dil, shift_a, 9, 128};
           probe<<<sms, 128, smem>>>(c, out);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("CUDA error: %s (N=%d rb=%d dil=%d)\n", cudaGetErrorString(e), N, rb, dil); return 1; }
