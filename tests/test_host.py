@@ -78,6 +78,13 @@ def test_s2mel_config_struct_layout_matches_header(tmp_path):
     if not torch.cuda.is_available():
         c.dilation_rate = 1
         assert lib.bvg_s2mel_tail_create(ctypes.byref(c), ctypes.byref(h)) in (-5, -4) and not h.value   # no device: no fallback
+    tm = importlib.import_module("voice-tts_b200.s2mel_tail")
+    cfgm = importlib.import_module("voice-tts_b200.config")
+    tail = tm.S2MelTail(cfgm.s2mel_tail_config(hidden=32, dit_hidden=32, n_layers=1), precision="fp32")
+    with pytest.raises(RuntimeError):          # CPU tensors: the host mirror has no torch fallback either
+        tail(torch.zeros(1, 8, 32), None, torch.zeros(1), torch.zeros(1, 32))
+    with pytest.raises(RuntimeError):
+        tm.euler_step_(torch.zeros(1, 4, 8), torch.zeros(2, 4, 8), 0.1, 0.7, 0)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
