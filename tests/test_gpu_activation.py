@@ -52,10 +52,13 @@ def test_act1d_golden_fp32(golden, act_mod, case):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 2, 3), (3, 2, 5), (2, 3, 6), (1, 7, 129), (2, 4, 4096),
-                                   (1, 3, 7809), (1, 2, 7937), (1, 2, 15872), (1, 2, 20003), (2, 2, 31232)])
+                                   (1, 3, 7809), (1, 2, 7937), (1, 2, 15872), (1, 2, 20003), (2, 2, 31232),
+                                   (1, 2, 4352), (1, 2, 4608), (1, 1, 4609), (1, 1, 4864), (1, 2, 7936), (1, 1, 7940), (1, 1, 131075)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_act1d_bct_shapes(ops, shape, dtype):
-    """ragged / tiny / tile-boundary lengths, aligned (bulk-copy) and unaligned paths"""
+    """ragged / tiny / tile-boundary lengths, aligned (bulk-copy) and unaligned paths; fp32 tiles longer than ~4 500 samples take
+    the in-place kernel (one tile buffer), shorter ones and 16-bit I/O the two-buffer kernel - both sides of that switch, a full
+    7 936-sample tile, a tile of 4 samples behind it and a 17-tile row are in the list"""
     B, C, T = shape
     g = torch.Generator().manual_seed(B * 1000 + C * 100 + T)
     x = (torch.randn(B, C, T, generator=g) * 2).to(dtype)
